@@ -1,0 +1,79 @@
+"""ctypes loader for the C-ABI shared library (include/sealfm.h, include/sealdec.h).
+
+The library is the product; there is NO Python/CPU fallback.  If libsealb200.so is missing or a
+symbol cannot be resolved, importing this module raises — loudly, on purpose.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsealb200.so")
+
+u64 = C.c_uint64
+u32 = C.c_uint32
+i32 = C.c_int
+vp = C.c_void_p
+cp = C.c_char_p
+
+
+class SealB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[sealb200 {code}] {msg}")
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C seal_b200/csrc`. seal_b200 has no CPU fallback.")
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+# name -> (restype, argtypes); mirrors include/sealfm.h one to one
+_FM_SIGS = {
+    "sealfm_last_error": (cp, []),
+    "sealfm_abi_version": (i32, []),
+    "sealfm_build": (i32, [vp, u64, C.POINTER(vp)]),
+    "sealfm_build_from_file": (i32, [cp, i32, C.POINTER(vp)]),
+    "sealfm_load": (i32, [cp, C.POINTER(vp)]),
+    "sealfm_save": (i32, [vp, cp]),
+    "sealfm_free": (None, [vp]),
+    "sealfm_size": (u64, [vp]),
+    "sealfm_sigma": (u64, [vp]),
+    "sealfm_max_level": (u32, [vp]),
+    "sealfm_section": (i32, [vp, i32, C.POINTER(C.POINTER(u64)), C.POINTER(u64)]),
+    "sealfm_to_device": (i32, [vp, i32]),
+    "sealfm_device": (i32, [vp]),
+    "sealfm_device_bytes": (u64, [vp]),
+    "sealfm_set_beginnings": (i32, [vp, vp, u64]),
+    "sealfm_backward_search_step": (i32, [vp, u64, vp, vp, vp, vp, vp]),
+    "sealfm_backward_search_multi": (i32, [vp, u64, vp, vp, vp, vp]),
+    "sealfm_distinct_count_multi": (i32, [vp, u64, vp, vp, vp, vp, u64]),
+    "sealfm_locate": (i32, [vp, u64, vp, vp]),
+    "sealfm_doc_index_from_rows": (i32, [vp, u64, vp, vp]),
+    "sealfm_extract_text": (i32, [vp, u64, vp, vp, vp, vp, u64]),
+    "sealfm_backward_search_step_d": (i32, [vp, vp, u64, vp, vp, vp, vp, vp]),
+    "sealfm_expand_mask_d": (i32, [vp, vp, u64, vp, vp, vp, u32, u32, u32]),
+}
+
+
+def _bind(sigs):
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: intended
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind(_FM_SIGS)
+
+
+def check(code):
+    if code != 0:
+        raise SealB200Error(code, lib.sealfm_last_error().decode(errors="replace"))
+
+
+def fm_symbols():
+    return list(_FM_SIGS)

@@ -1,0 +1,543 @@
+// CUDA kernels + C ABI (include/sealfm.h) of the FM-index path.  sm_100a only.
+#include "../../include/sealfm.h"
+#include "fm_device.cuh"
+#include "fm_host.hpp"
+#include "fm_layout.hpp"
+#include "common.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace sealb200;
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct sealfm {
+    HostIndex host;
+    int device = -1;
+    FmView view{};                 // device pointers
+    void* d_blocks = nullptr;
+    uint64_t* d_csym = nullptr;
+    uint64_t* d_node_ones = nullptr;
+    uint64_t* d_sa = nullptr;
+    uint64_t* d_isa = nullptr;
+    uint64_t* d_beginnings = nullptr;
+    uint64_t device_bytes = 0;
+    std::vector<uint64_t> beginnings;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// Batched LF step (FMIndex::backward_search_step, fm_index.cpp:67-76): one thread per triple.
+__global__ void __launch_bounds__(256) lf_step_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ sym,
+                                                      const uint64_t* __restrict__ lo,
+                                                      const uint64_t* __restrict__ hi,
+                                                      uint64_t* __restrict__ out_lo,
+                                                      uint64_t* __restrict__ out_hi) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t l, r;
+        lf_step(v, sym[t], lo[t], hi[t], l, r);
+        out_lo[t] = l;
+        out_hi[t] = r;
+    }
+}
+
+// FMIndex::backward_search_multi (fm_index.cpp:55-65): fold from (0, size()), return {l, r+1}.
+__global__ void __launch_bounds__(128) lf_fold_kernel(FmView v, uint64_t nq, const uint64_t* __restrict__ symbols,
+                                                      const uint64_t* __restrict__ offsets,
+                                                      uint64_t* __restrict__ out_lo,
+                                                      uint64_t* __restrict__ out_hi) {
+    for (uint64_t q = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; q < nq; q += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t l = 0, r = v.m;
+        for (uint64_t t = offsets[q]; t < offsets[q + 1]; ++t) lf_step(v, symbols[t], l, r, l, r);
+        out_lo[q] = l;
+        out_hi[q] = r + 1;
+    }
+}
+
+struct MaskSink {
+    uint32_t* row;        // bitmask row
+    uint32_t vocab, shift;
+    __device__ void operator()(uint32_t symbol, uint64_t, uint64_t) const {
+        // seal/index.py:141,153: the sentinel (0) is dropped, tokens are symbol - SHIFT
+        if (symbol < shift || symbol == 0) return;
+        const uint32_t tok = symbol - shift;
+        if (tok < vocab) atomicOr(row + (tok >> 5), 1u << (tok & 31));
+    }
+};
+struct DenseSink {
+    uint64_t* counts;     // 2^L entries for this range, zeroed
+    __device__ void operator()(uint32_t symbol, uint64_t ri, uint64_t rj) const { counts[symbol] = rj - ri; }
+};
+
+// One warp expands one SA range.  Phase 1: level-synchronous frontier expansion, one lane per
+// frontier node, children compacted in order with a shuffle scan (frontier lives in shared memory).
+// Phase 2: once the frontier is wider than a warp, every lane walks its own subtrees depth-first.
+struct WarpFrontier {
+    uint64_t i[2][64];
+    uint64_t j[2][64];
+    uint32_t prefix[2][64];
+};
+
+template <typename Sink>
+__device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, WarpFrontier& F) {
+    if (lo >= hi) return;                                  // fm_index.cpp:98 `if (low == high) return`
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t L = v.L;
+    uint32_t n = 1, level = 0, cur = 0;
+    if (lane == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; }
+    __syncwarp();
+    while (level < L && n <= 32) {
+        uint32_t nc = 0;
+        uint64_t a = 0, b = 0, ei = 0, ej = 0;
+        uint32_t ep = 0;
+        bool has0 = false, has1 = false;
+        if (lane < n) {
+            ei = F.i[cur][lane]; ej = F.j[cur][lane]; ep = F.prefix[cur][lane];
+            const uint64_t start = v.csym[static_cast<uint64_t>(ep) << (L - level)];
+            const uint64_t o1 = v.node_ones[(1u << level) + ep];
+            const uint64_t base = static_cast<uint64_t>(level) * v.m + start;
+            if (ej == ei + 1) {
+                int bit;
+                a = rank1(v, base + ei, &bit) - o1;
+                b = a + static_cast<uint64_t>(bit);
+            } else {
+                a = rank1(v, base + ei) - o1;
+                b = rank1(v, base + ej) - o1;
+            }
+            has1 = (b - a) != 0;
+            has0 = ((ej - ei) - (b - a)) != 0;
+            nc = (has0 ? 1u : 0u) + (has1 ? 1u : 0u);
+        }
+        uint32_t incl = nc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (uint32_t)d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t w = incl - nc;
+        const uint32_t nxt = cur ^ 1;
+        if (has0) { F.i[nxt][w] = ei - a; F.j[nxt][w] = ej - b; F.prefix[nxt][w] = ep << 1; ++w; }
+        if (has1) { F.i[nxt][w] = a; F.j[nxt][w] = b; F.prefix[nxt][w] = (ep << 1) | 1u; }
+        __syncwarp();
+        cur = nxt; n = total; ++level;
+    }
+    for (uint32_t e = lane; e < n; e += 32)
+        expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+}
+
+constexpr int kExpandWarps = 4;
+
+// Allowed-token bitmask rows for R ranges (seal/beam_search.py:107,131-135).  mask is zeroed here.
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_mask_kernel(
+    FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
+    uint32_t* __restrict__ mask, uint32_t ld_words, uint32_t vocab, uint32_t shift) {
+    __shared__ WarpFrontier F[kExpandWarps];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
+        uint32_t* row = mask + r * ld_words;
+        for (uint32_t w = lane; w < ld_words; w += 32) row[w] = 0;
+        __syncwarp();
+        MaskSink sink{row, vocab, shift};
+        warp_expand(v, lo[r], hi[r], sink, F[warp]);
+        __syncwarp();
+    }
+}
+
+// Dense per-range symbol counts (scratch for the ordered (symbol,count) API output).
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_dense_kernel(
+    FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
+    uint64_t* __restrict__ dense) {
+    __shared__ WarpFrontier F[kExpandWarps];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint64_t stride = 1ULL << v.L;
+    for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
+        DenseSink sink{dense + r * stride};
+        warp_expand(v, lo[r], hi[r], sink, F[warp]);
+        __syncwarp();
+    }
+}
+
+// Ordered compaction of one dense count row into interleaved (symbol,count) pairs — one block per
+// range; out_off[r] is where range r's pairs start (in u64 units), out_len[r] receives 2k.
+__global__ void __launch_bounds__(256) compact_pairs_kernel(uint32_t L, const uint64_t* __restrict__ dense,
+                                                            const uint64_t* __restrict__ out_off,
+                                                            uint64_t* __restrict__ out,
+                                                            uint64_t* __restrict__ out_len) {
+    __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t carry;
+    const uint64_t r = blockIdx.x;
+    const uint64_t nsym = 1ULL << L;
+    const uint64_t* row = dense + r * nsym;
+    uint64_t* dst = out + out_off[r];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t basei = 0; basei < nsym; basei += blockDim.x) {
+        const uint64_t s = basei + threadIdx.x;
+        const uint64_t c = s < nsym ? row[s] : 0;
+        const uint32_t flag = c != 0;
+        const uint32_t ball = __ballot_sync(0xffffffffu, flag);
+        const uint32_t pre = __popc(ball & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[warp] = __popc(ball);
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+        for (uint32_t w = 0; w < blockDim.x / 32; ++w) { if (w < warp) woff += warp_tot[w]; tot += warp_tot[w]; }
+        const uint32_t pos = carry + woff + pre;
+        if (flag) { dst[2ULL * pos] = s; dst[2ULL * pos + 1] = c; }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_len[r] = 2ULL * carry;
+}
+
+__global__ void __launch_bounds__(128) locate_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ rows,
+                                                     uint64_t* __restrict__ out, int want_doc) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t pos = locate_row(v, rows[t]);
+        if (want_doc) pos = doc_of_pos(v, pos);
+        out[t] = pos;
+    }
+}
+
+__global__ void __launch_bounds__(64) extract_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ begins,
+                                                     const uint64_t* __restrict__ ends,
+                                                     const uint64_t* __restrict__ offs, uint64_t* __restrict__ out) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x)
+        extract_text(v, begins[t], ends[t], out + offs[t]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+int grid_for(uint64_t work_items, int per_block, int max_waves = 8) {
+    uint64_t blocks = (work_items + per_block - 1) / per_block;
+    uint64_t cap = (uint64_t)sm_count() * max_waves;       // multiples of the SM count (148 on B200)
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    return (int)blocks;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    explicit DevBuf(uint64_t n) { if (n) CUDA_CHECK(cudaMalloc(&p, n * sizeof(T))); }
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+void require_device(const sealfm_t* h) {
+    if (!h) throw ApiError(SEALFM_EINVAL, "null handle");
+    if (h->device < 0) throw ApiError(SEALFM_ENODEVICE, "index not bound to a CUDA device (call sealfm_to_device)");
+    CUDA_CHECK(cudaSetDevice(h->device));
+}
+
+void upload(sealfm_t* h, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        throw ApiError(SEALFM_ENODEVICE, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) throw ApiError(SEALFM_EINVAL, "bad device id");
+    CUDA_CHECK(cudaSetDevice(device));
+    const HostIndex& H = h->host;
+    const uint32_t L = H.max_level;
+    const uint64_t m = H.size;
+    DeviceArrays A;
+    make_device_arrays(H, A);
+    const std::vector<uint64_t>& blk = A.blocks;
+    const std::vector<uint64_t>& csym = A.csym;
+    const std::vector<uint64_t>& node_ones = A.node_ones;
+
+    auto put = [&](const void* src, uint64_t bytes) -> void* {
+        void* d = nullptr;
+        CUDA_CHECK(cudaMalloc(&d, bytes ? bytes : 8));
+        if (bytes) CUDA_CHECK(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+        h->device_bytes += bytes;
+        return d;
+    };
+    h->device_bytes = 0;
+    h->d_blocks = put(blk.data(), blk.size() * 8);
+    h->d_csym = (uint64_t*)put(csym.data(), csym.size() * 8);
+    h->d_node_ones = (uint64_t*)put(node_ones.data(), node_ones.size() * 8);
+    h->d_sa = (uint64_t*)put(H.sa_samples.data(), H.sa_samples.size() * 8);
+    h->d_isa = (uint64_t*)put(H.isa_samples.data(), H.isa_samples.size() * 8);
+    FmView& v = h->view;
+    v.blocks = (const uint4*)h->d_blocks;
+    v.csym = h->d_csym; v.node_ones = h->d_node_ones;
+    v.sa_samples = h->d_sa; v.isa_samples = h->d_isa;
+    v.n_isa = H.isa_samples.size();
+    v.beginnings = nullptr; v.n_beginnings = 0;
+    v.m = m; v.L = L;
+    h->device = device;
+    if (!h->beginnings.empty()) {
+        h->d_beginnings = (uint64_t*)put(h->beginnings.data(), h->beginnings.size() * 8);
+        v.beginnings = h->d_beginnings; v.n_beginnings = h->beginnings.size();
+    }
+}
+
+void release_device(sealfm_t* h) {
+    if (h->device < 0) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_blocks); cudaFree(h->d_csym); cudaFree(h->d_node_ones);
+    cudaFree(h->d_sa); cudaFree(h->d_isa); cudaFree(h->d_beginnings);
+    h->device = -1;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* sealfm_last_error(void) { return last_error().c_str(); }
+int sealfm_abi_version(void) { return 1; }
+
+int sealfm_build(const uint64_t* symbols, uint64_t n, sealfm_t** out) {
+    return guarded([&] {
+        if (!out || (!symbols && n)) throw ApiError(SEALFM_EINVAL, "null argument");
+        std::unique_ptr<sealfm> h(new sealfm());
+        build_index(symbols, n, h->host);
+        *out = h.release();
+    });
+}
+int sealfm_build_from_file(const char* path, int width_bytes, sealfm_t** out) {
+    return guarded([&] {
+        if (!out || !path) throw ApiError(SEALFM_EINVAL, "null argument");
+        std::unique_ptr<sealfm> h(new sealfm());
+        try { build_index_from_file(path, width_bytes, h->host); }
+        catch (const std::runtime_error& e) { throw ApiError(SEALFM_EIO, e.what()); }
+        *out = h.release();
+    });
+}
+int sealfm_load(const char* path, sealfm_t** out) {
+    return guarded([&] {
+        if (!out || !path) throw ApiError(SEALFM_EINVAL, "null argument");
+        std::unique_ptr<sealfm> h(new sealfm());
+        try { load_index(path, h->host); }
+        catch (const std::runtime_error& e) { throw ApiError(SEALFM_EIO, e.what()); }
+        *out = h.release();
+    });
+}
+int sealfm_save(const sealfm_t* h, const char* path) {
+    return guarded([&] {
+        if (!h || !path) throw ApiError(SEALFM_EINVAL, "null argument");
+        try { save_index_native(h->host, path); }
+        catch (const std::runtime_error& e) { throw ApiError(SEALFM_EIO, e.what()); }
+    });
+}
+void sealfm_free(sealfm_t* h) {
+    if (!h) return;
+    release_device(h);
+    delete h;
+}
+uint64_t sealfm_size(const sealfm_t* h) { return h ? h->host.size : 0; }
+uint64_t sealfm_sigma(const sealfm_t* h) { return h ? h->host.sigma : 0; }
+uint32_t sealfm_max_level(const sealfm_t* h) { return h ? h->host.max_level : 0; }
+
+int sealfm_section(const sealfm_t* h, int which, const uint64_t** ptr, uint64_t* n_words) {
+    return guarded([&] {
+        if (!h || !ptr || !n_words) throw ApiError(SEALFM_EINVAL, "null argument");
+        const std::vector<uint64_t>* v = nullptr;
+        switch (which) {
+            case 0: v = &h->host.tree; break;
+            case 1: v = &h->host.alphabet; break;
+            case 2: v = &h->host.C; break;
+            case 3: v = &h->host.sa_samples; break;
+            case 4: v = &h->host.isa_samples; break;
+            default: throw ApiError(SEALFM_EINVAL, "unknown section");
+        }
+        *ptr = v->data(); *n_words = v->size();
+    });
+}
+
+int sealfm_to_device(sealfm_t* h, int device) {
+    return guarded([&] {
+        if (!h) throw ApiError(SEALFM_EINVAL, "null handle");
+        if (h->device >= 0) release_device(h);
+        upload(h, device);
+    });
+}
+int sealfm_device(const sealfm_t* h) { return h ? h->device : -1; }
+uint64_t sealfm_device_bytes(const sealfm_t* h) { return h ? h->device_bytes : 0; }
+
+int sealfm_set_beginnings(sealfm_t* h, const uint64_t* beginnings, uint64_t n) {
+    return guarded([&] {
+        if (!h || (!beginnings && n)) throw ApiError(SEALFM_EINVAL, "null argument");
+        h->beginnings.assign(beginnings, beginnings + n);
+        if (h->device >= 0) {
+            CUDA_CHECK(cudaSetDevice(h->device));
+            if (h->d_beginnings) { cudaFree(h->d_beginnings); h->d_beginnings = nullptr; }
+            CUDA_CHECK(cudaMalloc(&h->d_beginnings, (n ? n : 1) * 8));
+            CUDA_CHECK(cudaMemcpy(h->d_beginnings, beginnings, n * 8, cudaMemcpyHostToDevice));
+            h->view.beginnings = h->d_beginnings; h->view.n_beginnings = n;
+        }
+    });
+}
+
+int sealfm_backward_search_step_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t n,
+                                  const uint64_t* sym_d, const uint64_t* lo_d, const uint64_t* hi_d,
+                                  uint64_t* out_lo_d, uint64_t* out_hi_d) {
+    return guarded([&] {
+        require_device(h);
+        if (!n) return;
+        lf_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(h->view, n, sym_d, lo_d, hi_d, out_lo_d, out_hi_d);
+        CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, const uint64_t* lo_d,
+                         const uint64_t* hi_d, uint32_t* mask_d, uint32_t ld_words, uint32_t vocab,
+                         uint32_t shift) {
+    return guarded([&] {
+        require_device(h);
+        if (!R) return;
+        if ((uint64_t)ld_words * 32 < vocab) throw ApiError(SEALFM_EINVAL, "ld_words too small for vocab");
+        expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, 0, (cudaStream_t)stream>>>(
+            h->view, R, lo_d, hi_d, mask_d, ld_words, vocab, shift);
+        CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int sealfm_backward_search_step(const sealfm_t* h, uint64_t n, const uint64_t* sym, const uint64_t* lo,
+                                const uint64_t* hi, uint64_t* out_lo, uint64_t* out_hi) {
+    return guarded([&] {
+        require_device(h);
+        if (!n) return;
+        DevBuf<uint64_t> d(5 * n);
+        CUDA_CHECK(cudaMemcpy(d.p, sym, n * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.p + n, lo, n * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(d.p + 2 * n, hi, n * 8, cudaMemcpyHostToDevice));
+        lf_step_kernel<<<grid_for(n, 256), 256>>>(h->view, n, d.p, d.p + n, d.p + 2 * n, d.p + 3 * n, d.p + 4 * n);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpy(out_lo, d.p + 3 * n, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(out_hi, d.p + 4 * n, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sealfm_backward_search_multi(const sealfm_t* h, uint64_t nq, const uint64_t* symbols,
+                                 const uint64_t* offsets, uint64_t* out_lo, uint64_t* out_hi) {
+    return guarded([&] {
+        require_device(h);
+        if (!nq) return;
+        const uint64_t tot = offsets[nq];
+        DevBuf<uint64_t> ds(tot), doff(nq + 1), dout(2 * nq);
+        if (tot) CUDA_CHECK(cudaMemcpy(ds.p, symbols, tot * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(doff.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice));
+        lf_fold_kernel<<<grid_for(nq, 128), 128>>>(h->view, nq, ds.p, doff.p, dout.p, dout.p + nq);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpy(out_lo, dout.p, nq * 8, cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaMemcpy(out_hi, dout.p + nq, nq * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* lows, const uint64_t* highs,
+                                uint64_t* out_offsets, uint64_t* out, uint64_t out_cap) {
+    return guarded([&] {
+        require_device(h);
+        if (!out_offsets || (!lows && n) || (!highs && n)) throw ApiError(SEALFM_EINVAL, "null argument");
+        const uint32_t L = h->host.max_level;
+        const uint64_t nsym = 1ULL << L;
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(64, (1ULL << 25) / (nsym * 8)));
+        std::vector<uint64_t> lens(n, 0);
+        std::vector<std::vector<uint64_t>> pieces;      // per chunk: packed results (upper-bound layout)
+        std::vector<std::vector<uint64_t>> piece_off;
+        pieces.reserve((n + chunk - 1) / chunk);
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, n - c0);
+            std::vector<uint64_t> ub(cn + 1, 0);        // upper bound on 2k per range
+            for (uint64_t i = 0; i < cn; ++i) {
+                uint64_t lo = lows[c0 + i], hi = highs[c0 + i];
+                // hi == size()+1 is reachable through the reference's first-step quirk;
+                // the arithmetic below is the reference's own for such a range.
+                if (hi > h->host.size + 1) throw ApiError(SEALFM_EINVAL, "range end beyond size()+1");
+                uint64_t k = hi > lo ? std::min<uint64_t>(hi - lo, nsym) : 0;
+                ub[i + 1] = ub[i] + 2 * k;
+            }
+            DevBuf<uint64_t> dlo(cn), dhi(cn), ddense(cn * nsym), doff(cn + 1), dout(ub[cn]), dlen(cn);
+            CUDA_CHECK(cudaMemcpy(dlo.p, lows + c0, cn * 8, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(dhi.p, highs + c0, cn * 8, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemcpy(doff.p, ub.data(), (cn + 1) * 8, cudaMemcpyHostToDevice));
+            CUDA_CHECK(cudaMemset(ddense.p, 0, cn * nsym * 8));
+            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32>>>(h->view, cn, dlo.p, dhi.p, ddense.p);
+            CUDA_CHECK(cudaGetLastError());
+            compact_pairs_kernel<<<(unsigned)cn, 256>>>(L, ddense.p, doff.p, dout.p, dlen.p);
+            CUDA_CHECK(cudaGetLastError());
+            pieces.emplace_back(ub[cn]);
+            if (ub[cn]) CUDA_CHECK(cudaMemcpy(pieces.back().data(), dout.p, ub[cn] * 8, cudaMemcpyDeviceToHost));
+            CUDA_CHECK(cudaMemcpy(lens.data() + c0, dlen.p, cn * 8, cudaMemcpyDeviceToHost));
+            piece_off.push_back(std::move(ub));
+        }
+        out_offsets[0] = 0;
+        for (uint64_t i = 0; i < n; ++i) out_offsets[i + 1] = out_offsets[i] + lens[i];
+        if (!out) return;
+        if (out_offsets[n] > out_cap) throw ApiError(SEALFM_ECAPACITY, "output buffer too small");
+        for (uint64_t c0 = 0, pc = 0; c0 < n; c0 += chunk, ++pc) {
+            const uint64_t cn = std::min(chunk, n - c0);
+            for (uint64_t i = 0; i < cn; ++i)
+                if (lens[c0 + i])
+                    std::memcpy(out + out_offsets[c0 + i], pieces[pc].data() + piece_off[pc][i], lens[c0 + i] * 8);
+        }
+    });
+}
+
+static int locate_impl(const sealfm_t* h, uint64_t n, const uint64_t* rows, uint64_t* out, int want_doc) {
+    return guarded([&] {
+        require_device(h);
+        if (!n) return;
+        if (want_doc && !h->view.beginnings) throw ApiError(SEALFM_EINVAL, "sealfm_set_beginnings not called");
+        DevBuf<uint64_t> d(2 * n);
+        CUDA_CHECK(cudaMemcpy(d.p, rows, n * 8, cudaMemcpyHostToDevice));
+        locate_kernel<<<grid_for(n, 128), 128>>>(h->view, n, d.p, d.p + n, want_doc);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaMemcpy(out, d.p + n, n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+int sealfm_locate(const sealfm_t* h, uint64_t n, const uint64_t* rows, uint64_t* out_pos) {
+    return locate_impl(h, n, rows, out_pos, 0);
+}
+int sealfm_doc_index_from_rows(const sealfm_t* h, uint64_t n, const uint64_t* rows, uint64_t* out_doc) {
+    return locate_impl(h, n, rows, out_doc, 1);
+}
+
+int sealfm_extract_text(const sealfm_t* h, uint64_t n, const uint64_t* begins, const uint64_t* ends,
+                        uint64_t* out_offsets, uint64_t* out, uint64_t out_cap) {
+    return guarded([&] {
+        require_device(h);
+        if (!out_offsets) throw ApiError(SEALFM_EINVAL, "null argument");
+        out_offsets[0] = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (ends[i] >= h->host.size || begins[i] > ends[i]) throw ApiError(SEALFM_EINVAL, "bad text interval");
+            out_offsets[i + 1] = out_offsets[i] + (ends[i] - begins[i]);
+        }
+        if (!out || !n) return;
+        const uint64_t tot = out_offsets[n];
+        if (tot > out_cap) throw ApiError(SEALFM_ECAPACITY, "output buffer too small");
+        DevBuf<uint64_t> db(n), de(n), doff(n + 1), dout(tot);
+        CUDA_CHECK(cudaMemcpy(db.p, begins, n * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(de.p, ends, n * 8, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(doff.p, out_offsets, (n + 1) * 8, cudaMemcpyHostToDevice));
+        extract_kernel<<<grid_for(n, 64), 64>>>(h->view, n, db.p, de.p, doff.p, dout.p);
+        CUDA_CHECK(cudaGetLastError());
+        if (tot) CUDA_CHECK(cudaMemcpy(out, dout.p, tot * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

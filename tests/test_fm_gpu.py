@@ -1,0 +1,173 @@
+"""GPU parity: the CUDA FM-index kernels, called through the C ABI (include/sealfm.h) exactly as
+the reference's SWIG module would be, against the CPU oracle on the same seeded inputs; bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = np.load(os.path.join(HERE, "golden", "fm_golden.npz"))
+CASES = ["keeper", "toy", "rand5k", "phrase"]
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+
+
+def mk(text):
+    from seal_b200.cpp_modules.fm_index import FMIndex
+    fm = FMIndex(); fm.initialize(text)
+    return fm
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_goldens_through_the_abi(name):
+    fm = mk(G[f"{name}.text"])
+    size = int(G[f"{name}.size"])
+    assert fm.size() == size
+    fl, fh = G[f"{name}.first_lo"], G[f"{name}.first_hi"]
+    syms = np.arange(len(fl), dtype=np.uint64)
+    ol, oh = fm.backward_search_step_batch(syms, np.zeros_like(syms), np.full_like(syms, size))
+    assert np.array_equal(ol, fl) and np.array_equal(oh, fh)          # incl. the §H1 quirk
+    assert fm.backward_search_step(int(syms[-1]), 0, size) == [int(fl[-1]), int(fh[-1])]
+    wsym, wlo, whi = G[f"{name}.walk_sym"], G[f"{name}.walk_lo"], G[f"{name}.walk_hi"]
+    dc_off, dc = G[f"{name}.dc_off"], G[f"{name}.dc"]
+    W, D = wsym.shape
+    cl = np.zeros(W, dtype=np.uint64); ch = np.full(W, size, dtype=np.uint64)
+    for d in range(D):
+        a, b = fm.backward_search_step_batch(wsym[:, d], cl, ch)
+        assert np.array_equal(a, wlo[:, d]) and np.array_equal(b, whi[:, d])
+        cl, ch = a, b
+    # backward_search_multi == fold of steps, returns hi exclusive (fm_index.cpp:55-65)
+    lo_m, hi_m = fm.backward_search_multi_batch([wsym[w].tolist() for w in range(W)])
+    assert np.array_equal(lo_m, wlo[:, -1]) and np.array_equal(hi_m, whi[:, -1] + 1)
+    assert fm.backward_search_multi(wsym[0].tolist()) == [int(wlo[0, -1]), int(whi[0, -1]) + 1]
+    # distinct_count over every visited range, one multi call
+    lows = wlo.reshape(-1); highs = whi.reshape(-1) + 1
+    ok = highs >= lows
+    res = fm.distinct_count_multi(lows[ok].tolist(), highs[ok].tolist())
+    ks = np.nonzero(ok)[0]
+    for r, k in zip(res, ks):
+        assert np.array_equal(np.asarray(r, dtype=np.uint64), dc[int(dc_off[k]):int(dc_off[k + 1])]), k
+    got = fm.locate_batch(G[f"{name}.loc_rows"])
+    assert np.array_equal(got, G[f"{name}.loc"])
+    assert fm.locate(int(size + 5)) == 2**64 - 1                        # fm_index.cpp:165
+    eo, ex = G[f"{name}.ext_off"], G[f"{name}.ext"]
+    for i, (b, e) in enumerate(zip(G[f"{name}.ext_b"], G[f"{name}.ext_e"])):
+        assert fm.extract_text(int(b), int(e)) == ex[int(eo[i]):int(eo[i + 1])].tolist()
+
+
+def test_sdsl_fmi_from_reference_answers_like_the_reference():
+    from seal_b200.cpp_modules.fm_index import load_FMIndex
+    fm = load_FMIndex(os.path.join(HERE, "golden", "tiny_ref.fmi"))
+    size = int(G["phrase.size"])
+    syms = np.arange(len(G["phrase.first_lo"]), dtype=np.uint64)
+    ol, oh = fm.backward_search_step_batch(syms, np.zeros_like(syms), np.full_like(syms, size))
+    assert np.array_equal(ol, G["phrase.first_lo"]) and np.array_equal(oh, G["phrase.first_hi"])
+    assert np.array_equal(fm.locate_batch(G["phrase.loc_rows"]), G["phrase.loc"])
+
+
+def test_corpus_walks_masks_and_docs_vs_oracle(small_corpus):
+    """80 k-token phrase corpus: the seal/index.py-level API, the batched kernels and the mask
+    expansion against the oracle (compiled reference when shipped, else the C port)."""
+    import torch
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.index import FMIndex
+    docs = small_corpus
+    seqs = [d.tolist() for d in docs]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs, in_memory=True)
+    idx2 = FMIndex(); idx2.initialize(seqs, in_memory=False)             # file path, '<l' ints
+    assert np.array_equal(idx.section(0), idx2.section(0))
+    assert len(idx) == len(ora) and idx.n_docs == ora.n_docs and idx.size() == ora.size()
+    assert idx.occurring_distinct == ora.occurring_distinct                # §H2 semantics
+    assert idx.occurring_counts == ora.occurring_counts
+    assert sorted(idx.occurring) == sorted(ora.occurring)
+    assert idx.get_range([]) == ora.get_range([])
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        d = seqs[int(rng.integers(0, len(seqs)))]
+        a = int(rng.integers(0, len(d) - 6)); n = int(rng.integers(1, 6))
+        seq = d[a:a + n]
+        assert idx.get_range(seq) == ora.get_range(seq)
+        assert idx.get_count(seq) == ora.get_count(seq)
+        assert idx.get_continuations(seq) == ora.get_continuations(seq)
+        lo, hi = ora.get_range(seq)
+        assert idx.get_distinct_count(lo, hi) == ora.get_distinct_count(lo, hi)
+        rows = list(range(lo, min(hi, lo + 5)))
+        assert [idx.get_doc_index_from_row(r) for r in rows] == [ora.get_doc_index_from_row(r) for r in rows]
+        assert idx.get_doc_index_from_rows(rows).tolist() == [ora.get_doc_index_from_row(r) for r in rows]
+        assert list(idx.get_doc_indices(seq))[:5] == [ora.get_doc_index_from_row(r) for r in rows]
+    for di in (0, 17, len(seqs) - 1):
+        assert idx.get_doc(di) == ora.get_doc(di) == seqs[di]
+    # unseen n-gram / unknown token
+    assert idx.get_count([4, 4, 4, 4, 4, 4, 4]) == ora.get_count([4, 4, 4, 4, 4, 4, 4])
+    assert idx.get_range([50264]) == ora.get_range([50264])
+    # device-tensor LF + mask expansion for a batch of live ranges
+    R = 512
+    toks = np.asarray([seqs[int(rng.integers(0, len(seqs)))][int(rng.integers(0, 30))] for _ in range(R)])
+    sym = torch.tensor(toks + 10, dtype=torch.int64, device="cuda")
+    lo0 = torch.zeros(R, dtype=torch.int64, device="cuda"); hi0 = torch.full((R,), idx.size(), dtype=torch.int64, device="cuda")
+    lo1, hi1 = idx.lf_step_tensors(sym, lo0, hi0)
+    exp = [ora.get_range([int(t)]) for t in toks]
+    assert lo1.tolist() == [e[0] for e in exp] and (hi1 + 1).tolist() == [e[1] for e in exp]
+    V = 50265
+    mask = idx.expand_mask_tensors(lo1, hi1 + 1, V).cpu().numpy().view(np.uint32)
+    for r in range(0, R, 7):
+        allowed = np.nonzero(np.unpackbits(mask[r].view(np.uint8), bitorder="little")[:V])[0].tolist()
+        assert allowed == ora.get_distinct(*exp[r]), r
+    # empty range and full range rows
+    lo2 = torch.tensor([5, 0], dtype=torch.int64, device="cuda"); hi2 = torch.tensor([5, len(idx)], dtype=torch.int64, device="cuda")
+    m2 = idx.expand_mask_tensors(lo2, hi2, V).cpu().numpy().view(np.uint32)
+    assert m2[0].sum() == 0
+    allowed = np.nonzero(np.unpackbits(m2[1].view(np.uint8), bitorder="little")[:V])[0].tolist()
+    assert allowed == ora.occurring_distinct
+    # save / load round trip keeps answers (index.py:186-204)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        idx.save(os.path.join(d, "ix"))
+        back = FMIndex.load(os.path.join(d, "ix"))
+        assert back.occurring_distinct == idx.occurring_distinct and back.beginnings == idx.beginnings
+        assert back.get_range(seqs[5][2:5]) == ora.get_range(seqs[5][2:5])
+
+
+def test_properties_at_scale():
+    """1 M-token corpus (oracle too slow to enumerate): size-independent properties of the kernels."""
+    import torch
+    from seal_b200.synthetic import make_corpus, corpus_symbols
+    from seal_b200.cpp_modules.fm_index import FMIndex
+    docs = make_corpus(n_docs=10_000, doc_len=100, n_phrases=20_000, seed=99)
+    text = corpus_symbols(docs)
+    fm = FMIndex(); fm.initialize(text)
+    m = fm.size()
+    assert m == text.size + 1
+    rng = np.random.default_rng(5)
+    # (1) counts of a range's distinct symbols sum to its width; symbols ascending
+    lows = rng.integers(0, m - 1, size=200); highs = np.minimum(lows + rng.integers(1, 5000, size=200), m)
+    for (lo, hi), r in zip(zip(lows, highs), fm.distinct_count_multi(lows.tolist(), highs.tolist())):
+        s, c = r[0::2], r[1::2]
+        assert sum(c) == hi - lo and s == sorted(s) and all(x > 0 for x in c)
+    # (2) LF of a range by every one of its distinct symbols partitions it: widths equal the counts
+    lo, hi = int(lows[0]), int(highs[0])
+    r = fm.distinct_count(lo, hi)
+    ol, oh = fm.backward_search_step_batch(r[0::2], [lo] * (len(r) // 2), [hi - 1] * (len(r) // 2))
+    assert ((oh + 1 - ol).tolist()) == r[1::2]
+    # (3) locate is a bijection rows -> text positions; inverse via extract of the whole text head
+    rows = rng.permutation(m)[:4000].astype(np.uint64)
+    pos = fm.locate_batch(rows)
+    assert len(set(pos.tolist())) == len(rows) and pos.max() < m
+    # (4) every document n-gram is found, and locate lands inside a document that contains it
+    for di in rng.integers(0, len(docs), size=20):
+        d = docs[di].tolist()
+        q = [t + 10 for t in d[10:14]]
+        lo, hi = fm.backward_search_multi(q)
+        assert hi > lo
+    # (5) extract_text round trip: reversed-text coordinates (seal/index.py:68-75)
+    n_tok = text.size
+    for di in (0, 5000, 9999):
+        got = fm.extract_text(di * 100, (di + 1) * 100)
+        assert [g - 10 for g in got] == docs[di].tolist()

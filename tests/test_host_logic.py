@@ -1,0 +1,156 @@
+"""CPU: host-side logic of the product — index construction, sdsl .fmi parsing, native container,
+C-ABI surface — plus the per-thread device primitives compiled for the host (tests/hostcheck)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.fm_oracle import PortFM
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+G = np.load(os.path.join(HERE, "golden", "fm_golden.npz"))
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    from seal_b200 import _lib
+    for hdr in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        text = open(os.path.join(ROOT, "include", hdr)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names = set(re.findall(r"\b(seal(?:fm|dec|bart)_[a-z0-9_]+)\s*\(", text))
+        assert names, hdr
+        for n in sorted(names):
+            assert hasattr(_lib.lib, n), f"{n} declared in include/{hdr} but not exported"
+    assert _lib.lib.sealfm_abi_version() >= 1
+
+
+def test_queries_fail_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from seal_b200.cpp_modules.fm_index import FMIndex
+    from seal_b200._lib import SealB200Error
+    fm = FMIndex(); fm.initialize(G["toy.text"])
+    with pytest.raises(SealB200Error) as e:
+        fm.backward_search_step(11, 0, fm.size())
+    assert e.value.code == -4
+
+
+@pytest.mark.parametrize("name", ["keeper", "toy", "rand5k", "phrase"])
+def test_builder_sections_equal_oracle_sections(name):
+    """SA-IS + level-wise WT (product, C++) vs prefix-doubling + sdsl-style WT (oracle, C):
+    tree bits, alphabet, C, SA/ISA samples must agree word for word."""
+    from seal_b200.cpp_modules.fm_index import FMIndex
+    text = G[f"{name}.text"]
+    fm = FMIndex(); fm.initialize(text)
+    p = PortFM(text)
+    assert fm.size() == p.size()
+    assert np.array_equal(fm.section(0), p.section("tree_words"))
+    assert np.array_equal(fm.section(1), p.section("alphabet"))
+    assert np.array_equal(fm.section(2), p.section("C"))
+    assert np.array_equal(fm.section(3), p.section("sa_samples"))
+    assert np.array_equal(fm.section(4), p.section("isa_samples"))
+
+
+def test_sdsl_fmi_written_by_reference_parses_to_the_same_sections(tmp_path):
+    """tests/golden/tiny_ref.fmi was written by the reference's FMIndex::save (sdsl store_to_file)."""
+    from seal_b200.cpp_modules.fm_index import FMIndex, load_FMIndex
+    ref = load_FMIndex(os.path.join(HERE, "golden", "tiny_ref.fmi"))
+    own = FMIndex(); own.initialize(G["phrase.text"])
+    assert ref.size() == own.size()
+    for s in range(5):
+        assert np.array_equal(ref.section(s), own.section(s)), s
+    # native container round trip
+    p = str(tmp_path / "x.fmi")
+    own.save(p)
+    back = load_FMIndex(p)
+    for s in range(5):
+        assert np.array_equal(back.section(s), own.section(s)), s
+
+
+def test_build_from_file_matches_in_memory(tmp_path):
+    from seal_b200.cpp_modules.fm_index import FMIndex
+    text = G["rand5k.text"]
+    p = tmp_path / "t.bin"
+    text.astype("<i4").tofile(p)
+    a = FMIndex(); a.initialize_from_file(str(p), 4)
+    b = FMIndex(); b.initialize(text)
+    for s in range(5):
+        assert np.array_equal(a.section(s), b.section(s))
+
+
+def test_bad_inputs_return_errors_not_aborts(tmp_path):
+    from seal_b200.cpp_modules.fm_index import FMIndex, load_FMIndex
+    from seal_b200._lib import SealB200Error
+    with pytest.raises(SealB200Error):
+        load_FMIndex(str(tmp_path / "missing.fmi"))
+    junk = tmp_path / "junk.fmi"; junk.write_bytes(b"\x01" * 100)
+    with pytest.raises(SealB200Error):
+        load_FMIndex(str(junk))
+    with pytest.raises(SealB200Error):
+        FMIndex().initialize([5, 0, 7])          # 0 is the sentinel
+    with pytest.raises(RuntimeError):
+        FMIndex().size()
+
+
+# ---- per-thread device primitives, compiled for the host -------------------------------------------
+@pytest.fixture(scope="module")
+def hostcheck():
+    so = os.path.join(HERE, "hostcheck", "libhostcheck.so")
+    srcs = [os.path.join(HERE, "hostcheck", "hostcheck.cpp"), os.path.join(ROOT, "seal_b200", "csrc", "fm_host.cpp")]
+    deps = srcs + [os.path.join(ROOT, "seal_b200", "csrc", f) for f in ("fm_device.cuh", "fm_layout.hpp", "fm_host.hpp", "sais.hpp")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", so] + srcs +
+                              ["-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL"])
+    L = C.CDLL(so)
+    u64, vp = C.c_uint64, C.c_void_p
+    L.hc_build.restype = vp; L.hc_build.argtypes = [vp, u64]
+    L.hc_load.restype = vp; L.hc_load.argtypes = [C.c_char_p]
+    L.hc_free.argtypes = [vp]
+    L.hc_size.restype = u64; L.hc_size.argtypes = [vp]
+    L.hc_lf_step.argtypes = [vp, u64, vp, vp, vp, vp, vp]
+    L.hc_distinct_count.restype = u64; L.hc_distinct_count.argtypes = [vp, u64, u64, vp, u64]
+    L.hc_locate.restype = u64; L.hc_locate.argtypes = [vp, u64]
+    L.hc_extract.argtypes = [vp, u64, u64, vp]
+    return L
+
+
+@pytest.mark.parametrize("name", ["keeper", "toy", "rand5k", "phrase"])
+def test_device_primitives_on_host_match_goldens(hostcheck, name):
+    L = hostcheck
+    text = np.ascontiguousarray(G[f"{name}.text"])
+    h = L.hc_build(text.ctypes.data, len(text))
+    assert h
+    size = int(G[f"{name}.size"])
+    fl, fh = G[f"{name}.first_lo"], G[f"{name}.first_hi"]
+    syms = np.arange(len(fl), dtype=np.uint64)
+    lo = np.zeros_like(syms); hi = np.full_like(syms, size)
+    ol = np.zeros_like(syms); oh = np.zeros_like(syms)
+    L.hc_lf_step(h, len(syms), syms.ctypes.data, lo.ctypes.data, hi.ctypes.data, ol.ctypes.data, oh.ctypes.data)
+    assert np.array_equal(ol, fl) and np.array_equal(oh, fh)
+    wsym, wlo, whi = G[f"{name}.walk_sym"], G[f"{name}.walk_lo"], G[f"{name}.walk_hi"]
+    dc_off, dc = G[f"{name}.dc_off"], G[f"{name}.dc"]
+    W, D = wsym.shape
+    cl = np.zeros(W, dtype=np.uint64); ch = np.full(W, size, dtype=np.uint64)
+    buf = np.zeros(1 << 18, dtype=np.uint64)
+    for d in range(D):
+        sy = np.ascontiguousarray(wsym[:, d])
+        a = np.zeros(W, dtype=np.uint64); b = np.zeros(W, dtype=np.uint64)
+        L.hc_lf_step(h, W, sy.ctypes.data, cl.ctypes.data, ch.ctypes.data, a.ctypes.data, b.ctypes.data)
+        assert np.array_equal(a, wlo[:, d]) and np.array_equal(b, whi[:, d])
+        cl, ch = a, b
+        for w in range(W):
+            k = w * D + d
+            got = L.hc_distinct_count(h, int(a[w]), int(b[w]) + 1, buf.ctypes.data, len(buf)) if int(b[w]) + 1 >= int(a[w]) else 0
+            assert np.array_equal(buf[:got], dc[int(dc_off[k]):int(dc_off[k + 1])])
+    for row, exp in zip(G[f"{name}.loc_rows"], G[f"{name}.loc"]):
+        assert L.hc_locate(h, int(row)) == int(exp)
+    eo, ex = G[f"{name}.ext_off"], G[f"{name}.ext"]
+    for i, (b, e) in enumerate(zip(G[f"{name}.ext_b"], G[f"{name}.ext_e"])):
+        o = np.zeros(max(int(e) - int(b), 1), dtype=np.uint64)
+        L.hc_extract(h, int(b), int(e), o.ctypes.data)
+        assert np.array_equal(o[: int(e) - int(b)], ex[int(eo[i]):int(eo[i + 1])])
+    L.hc_free(h)
