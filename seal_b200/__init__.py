@@ -5,5 +5,6 @@ Mirrors ``seal/__init__.py:7-9`` for the hot path: ``FMIndex``, ``fm_index_gener
 is no CPU fallback.
 """
 from .index import FMIndex  # noqa: F401
+from .beam_search import fm_index_generate, IndexBasedLogitsProcessor, SealBartEngine  # noqa: F401
 
-__all__ = ["FMIndex"]
+__all__ = ["FMIndex", "fm_index_generate", "IndexBasedLogitsProcessor", "SealBartEngine"]

@@ -60,6 +60,50 @@ _FM_SIGS = {
 }
 
 
+f32p = C.POINTER(C.c_float)
+
+
+class ProcessorCfg(C.Structure):          # sealdec_processor_cfg_t
+    _fields_ = [("num_beams", C.c_int32), ("pad_token_id", C.c_int32), ("eos_token_id", C.c_int32),
+                ("stop_at_count", C.c_int32), ("always_allow_eos", C.c_int32), ("forced_bos_token_id", C.c_int32),
+                ("n_force_decoding_from", C.c_int32), ("force_decoding_from", C.POINTER(C.c_int64)),
+                ("shift", C.c_int32)]
+
+
+class BartConfig(C.Structure):            # sealbart_config_t
+    _fields_ = [("vocab_size", C.c_int32), ("d_model", C.c_int32), ("encoder_layers", C.c_int32),
+                ("decoder_layers", C.c_int32), ("heads", C.c_int32), ("ffn_dim", C.c_int32),
+                ("max_positions", C.c_int32), ("scale_embedding", C.c_int32), ("gemm_mode", C.c_int32)]
+
+
+class DecParams(C.Structure):             # sealdec_params_t
+    _fields_ = [("num_beams", C.c_int32), ("min_length", C.c_int32), ("max_length", C.c_int32),
+                ("length_penalty", C.c_float), ("eos_token_id", C.c_int32), ("pad_token_id", C.c_int32),
+                ("decoder_start_token_id", C.c_int32), ("model_eos_token_id", C.c_int32),
+                ("forced_eos_token_id", C.c_int32), ("forced_bos_token_id", C.c_int32),
+                ("stop_at_count", C.c_int32), ("always_allow_eos", C.c_int32), ("disable_fm_index", C.c_int32),
+                ("remove_invalid_values", C.c_int32), ("n_force_decoding_from", C.c_int32),
+                ("force_decoding_from", C.POINTER(C.c_int64)), ("shift", C.c_int32)]
+
+
+_DEC_SIGS = {
+    "sealdec_apply_index_mask_d": (i32, [vp, vp, C.POINTER(ProcessorCfg), vp, C.c_int64, C.c_int64, vp, vp, vp,
+                                         C.c_int64, C.c_int64]),
+    "sealbart_create": (i32, [C.POINTER(BartConfig), i32, C.POINTER(vp)]),
+    "sealbart_free": (None, [vp]),
+    "sealbart_set_tensor": (i32, [vp, cp, vp, u64]),
+    "sealbart_finalize": (i32, [vp]),
+    "sealbart_device_bytes": (u64, [vp]),
+    "sealdec_hyps_per_query": (C.c_int64, [C.POINTER(DecParams)]),
+    "sealdec_generate": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),
+    "sealdec_generate_d": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp,
+                                 vp, vp, vp]),
+    "sealdec_debug_step_logits": (i32, [vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, vp]),
+    "sealdec_last_launch_count": (C.c_int64, [vp]),
+    "sealdec_last_phase_us": (i32, [vp, C.POINTER(C.c_double)]),
+}
+
+
 def _bind(sigs):
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing: intended
@@ -68,6 +112,7 @@ def _bind(sigs):
 
 
 _bind(_FM_SIGS)
+_bind(_DEC_SIGS)
 
 
 def check(code):

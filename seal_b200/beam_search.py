@@ -1,0 +1,254 @@
+"""Drop-in for ``seal.beam_search`` (/root/reference/seal/beam_search.py) on the B200 kernels.
+
+* ``IndexBasedLogitsProcessor`` — same constructor, attributes and HF ``LogitsProcessor`` protocol
+  (``__call__(input_ids, scores) -> scores + mask``, beam_search.py:33-140); the FM-index work and
+  the mask run as CUDA kernels on the tensors' device, no ``.tolist()`` / H2D round trips.
+* ``fm_index_generate`` — same signature and return value (beam_search.py:391-557) for the path
+  SEALSearcher uses (``keep_history=True``, one beam group, no sampling): encoder, every decoder
+  step, log-softmax, processors, FM-index constraint, top-k and BeamSearchScorerWithMemory all run
+  inside libsealb200.so.
+* ``SealBartEngine`` — device copy of an HF ``BartForConditionalGeneration``'s weights.
+
+No CPU path: CPU tensors are rejected.
+"""
+import ctypes as C
+import math
+import weakref
+from typing import List, Optional
+
+import numpy as np
+
+from ._lib import lib, check, vp, ProcessorCfg, BartConfig, DecParams
+from .index import FMIndex, SHIFT
+
+stopword_token_ids = [10, 41, 660, 5, 1941, 20, 7, 6]      # beam_search.py:22-31
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _occurring_mask(index, vocab, device=None):
+    """uint32 bitmask of index.occurring_distinct (first-step rule, beam_search.py:73-77)."""
+    cache = index.__dict__.setdefault("_occ_cache", {})
+    key = (vocab, str(device))
+    if key not in cache:
+        words = np.zeros((vocab + 31) // 32, dtype=np.uint32)
+        toks = np.asarray([t for t in index.occurring_distinct if 0 <= t < vocab], dtype=np.int64)
+        np.bitwise_or.at(words, toks >> 5, (np.uint32(1) << (toks & 31).astype(np.uint32)))
+        if device is None:
+            cache[key] = words
+        else:
+            torch = _torch()
+            cache[key] = torch.from_numpy(words.view(np.int32)).to(device)
+    return cache[key]
+
+
+class IndexBasedLogitsProcessor:
+    """beam_search.py:33-140.  (Does not inherit transformers.LogitsProcessor so that importing the
+    drop-in never depends on the installed transformers version; HF only duck-types `__call__`.)"""
+
+    def __init__(self, index: FMIndex, num_beams: int, pad_token_id: int = 0, eos_token_id: int = 2,
+                 force_decoding_from: Optional[List[int]] = None, stop_at_count: int = 0,
+                 always_allow_eos: bool = False, forced_bos_token_id: Optional[int] = None):
+        self.index = index
+        self.pad_token_id = pad_token_id
+        self.eos_token_id = eos_token_id
+        self._num_beams = num_beams
+        self.log_odds_weight = 0.0
+        self.force_decoding_from = force_decoding_from
+        self.force_decoding_second_token = None
+        self.block_initial_stopwords = False
+        self.stop_at_count = stop_at_count
+        self.always_allow_eos = always_allow_eos
+        self.forced_bos_token_id = forced_bos_token_id
+
+    def __call__(self, input_ids, scores):
+        torch = _torch()
+        if not (scores.is_cuda and input_ids.is_cuda):
+            raise RuntimeError("seal_b200.IndexBasedLogitsProcessor runs on CUDA tensors only (no CPU fallback)")
+        if scores.dtype != torch.float32:
+            raise TypeError("scores must be float32 (the reference decodes in fp32)")
+        ids = input_ids.to(torch.int64).contiguous()
+        sc = scores.contiguous()
+        R, t = ids.shape
+        V = sc.shape[-1]
+        out = torch.empty_like(sc)
+        force = self.force_decoding_from or []
+        farr = (C.c_int64 * max(len(force), 1))(*force)
+        cfg = ProcessorCfg(self._num_beams, self.pad_token_id, self.eos_token_id, int(self.stop_at_count),
+                           int(bool(self.always_allow_eos)),
+                           -1 if self.forced_bos_token_id is None else int(self.forced_bos_token_id),
+                           len(force), farr, SHIFT)
+        with torch.cuda.device(sc.device):
+            occ = _occurring_mask(self.index, V, sc.device)
+            check(lib.sealdec_apply_index_mask_d(self.index._dev(), torch.cuda.current_stream().cuda_stream,
+                                                 C.byref(cfg), ids.data_ptr(), R, t, occ.data_ptr(),
+                                                 sc.data_ptr(), out.data_ptr(), V, sc.stride(0)))
+        return out
+
+
+class SealBartEngine:
+    """Device-resident BART weights + workspace (include/sealdec.h `sealbart_t`)."""
+
+    def __init__(self, state_dict, config, device=0, gemm_mode=0):
+        d = int(config.d_model)
+        self.config = config
+        self.device = int(device)
+        cfg = BartConfig(int(config.vocab_size), d, int(config.encoder_layers), int(config.decoder_layers),
+                         int(config.decoder_attention_heads), int(config.decoder_ffn_dim),
+                         int(config.max_position_embeddings), int(bool(getattr(config, "scale_embedding", False))),
+                         int(gemm_mode))
+        if config.encoder_ffn_dim != config.decoder_ffn_dim or config.encoder_attention_heads != config.decoder_attention_heads:
+            raise ValueError("encoder/decoder shapes must match (bart-large layout)")
+        if getattr(config, "activation_function", "gelu") != "gelu":
+            raise ValueError("only the exact-erf 'gelu' activation of bart-large is implemented")
+        h = vp()
+        check(lib.sealbart_create(C.byref(cfg), self.device, C.byref(h)))
+        self._h = h.value
+        for k, v in state_dict.items():
+            if k.endswith("embed_tokens.weight") and "model.shared.weight" in state_dict:
+                continue                                    # tied aliases of model.shared.weight
+            if k == "lm_head.weight" and "model.shared.weight" in state_dict and v.data_ptr() == state_dict["model.shared.weight"].data_ptr():
+                continue
+            a = np.ascontiguousarray(v.detach().to("cpu").float().numpy())
+            check(lib.sealbart_set_tensor(self._h, k.encode(), a.ctypes.data, a.size))
+        check(lib.sealbart_finalize(self._h))
+
+    @classmethod
+    def from_hf(cls, model, device=None, gemm_mode=0):
+        torch = _torch()
+        if device is None:
+            p = next(model.parameters())
+            device = p.device.index if p.is_cuda else torch.cuda.current_device()
+        return cls(model.state_dict(), model.config, device=device, gemm_mode=gemm_mode)
+
+    def __del__(self):
+        h = self.__dict__.get("_h")
+        if h:
+            lib.sealbart_free(h)
+            self._h = None
+
+    def device_bytes(self):
+        return int(lib.sealbart_device_bytes(self._h))
+
+    def debug_step_logits(self, input_ids, attention_mask, num_beams, decoder_input_ids):
+        """Teacher-forced logits of the last decoder position for explicit decoder inputs [R,t]."""
+        ids = np.ascontiguousarray(np.asarray(input_ids, dtype=np.int64))
+        am = np.ascontiguousarray(np.asarray(attention_mask, dtype=np.int64))
+        dec = np.ascontiguousarray(np.asarray(decoder_input_ids, dtype=np.int64))
+        Q, S = ids.shape
+        R, t = dec.shape
+        assert R == Q * num_beams
+        out = np.empty((R, int(self.config.vocab_size)), dtype=np.float32)
+        check(lib.sealdec_debug_step_logits(self._h, ids.ctypes.data, am.ctypes.data, Q, S, num_beams,
+                                            dec.ctypes.data, t, out.ctypes.data))
+        return out
+
+    def last_phase_us(self):
+        a = (C.c_double * 5)()
+        check(lib.sealdec_last_phase_us(self._h, a))
+        return {"encoder": a[0], "decoder_layers": a[1], "lm_head": a[2], "select_expand": a[3], "total": a[4]}
+
+    def last_launch_count(self):
+        return int(lib.sealdec_last_launch_count(self._h))
+
+
+_ENGINES = weakref.WeakKeyDictionary()
+
+
+def _engine_for(model):
+    if isinstance(model, SealBartEngine):
+        return model
+    eng = _ENGINES.get(model)
+    if eng is None:
+        eng = SealBartEngine.from_hf(model)
+        _ENGINES[model] = eng
+    return eng
+
+
+def _make_params(cfg, num_beams, min_length, max_length, length_penalty, eos_token_id, force_decoding_from,
+                 always_allow_eos, disable_fm_index, stop_at_count, forced_bos_token_id):
+    force = list(force_decoding_from or [])
+    farr = (C.c_int64 * max(len(force), 1))(*force)
+    none = lambda x: -1 if x is None else int(x)
+    p = DecParams(int(num_beams), int(min_length if min_length is not None else -1), int(max_length),
+                  float(length_penalty), int(eos_token_id), int(cfg.pad_token_id), int(cfg.decoder_start_token_id),
+                  none(cfg.eos_token_id), none(getattr(cfg, "forced_eos_token_id", None)), none(forced_bos_token_id),
+                  int(stop_at_count), int(bool(always_allow_eos)), int(bool(disable_fm_index)), 1, len(force), farr, SHIFT)
+    p._keepalive = farr
+    return p
+
+
+def generate_records(model, index, input_ids, attention_mask, min_length=3, max_length=25, length_penalty=1.0,
+                     num_beams=3, eos_token_id=None, force_decoding_from=None, always_allow_eos=False,
+                     disable_fm_index=False, stop_at_count=0, forced_bos_token_id="config", want_ranges=True):
+    """The C-ABI call with HOST buffers (sealdec_generate): returns the packed hypothesis records
+    (scores [Q,H] f32, lens [Q,H] i32, tokens [Q,H,T] i32, valid [Q,H] u8, lo/hi [Q,H] u64)."""
+    eng = _engine_for(model)
+    cfg = eng.config
+    if forced_bos_token_id == "config":
+        forced_bos_token_id = getattr(cfg, "forced_bos_token_id", None)
+    if eos_token_id is None:
+        eos_token_id = cfg.eos_token_id
+    ids = np.ascontiguousarray(np.asarray(input_ids.cpu() if hasattr(input_ids, "cpu") else input_ids, dtype=np.int64))
+    am = np.ascontiguousarray(np.asarray(attention_mask.cpu() if hasattr(attention_mask, "cpu") else attention_mask, dtype=np.int64))
+    Q, S = ids.shape
+    p = _make_params(cfg, num_beams, min_length, max_length, length_penalty, eos_token_id, force_decoding_from,
+                     always_allow_eos, disable_fm_index, stop_at_count, forced_bos_token_id)
+    H = int(lib.sealdec_hyps_per_query(C.byref(p)))
+    T = int(max_length)
+    scores = np.empty((Q, H), dtype=np.float32); lens = np.empty((Q, H), dtype=np.int32)
+    toks = np.empty((Q, H, T), dtype=np.int32); valid = np.empty((Q, H), dtype=np.uint8)
+    lo = np.zeros((Q, H), dtype=np.uint64) if want_ranges else None
+    hi = np.zeros((Q, H), dtype=np.uint64) if want_ranges else None
+    fm_h = None
+    occ_ptr = None
+    if not disable_fm_index:
+        if index._device is None:
+            index.to_device(eng.device)
+        fm_h = index._dev()
+        occ = _occurring_mask(index, int(cfg.vocab_size))
+        occ_ptr = occ.ctypes.data
+    check(lib.sealdec_generate(eng._h, fm_h, occ_ptr, C.byref(p), ids.ctypes.data, am.ctypes.data, Q, S,
+                               scores.ctypes.data, lens.ctypes.data, toks.ctypes.data, valid.ctypes.data,
+                               lo.ctypes.data if want_ranges else None, hi.ctypes.data if want_ranges else None))
+    return {"scores": scores, "lens": lens, "tokens": toks, "valid": valid, "lo": lo, "hi": hi}
+
+
+def records_to_output(rec, length_penalty):
+    """beam_search.py:555: [(score * len**lp, tokens) for every recorded hyp with score > -inf]."""
+    out = []
+    scores, lens, toks = rec["scores"], rec["lens"], rec["tokens"]
+    for q in range(scores.shape[0]):
+        s = scores[q].astype(np.float64).tolist(); l = lens[q].tolist(); t = toks[q].tolist()
+        row = []
+        for i in range(len(s)):
+            n = l[i]
+            sc = s[i] / (n ** length_penalty)                     # BeamHypothesesWithMemory.add, :752-755
+            if sc > float("-inf"):
+                row.append((sc * n ** length_penalty, t[i][:n]))
+        out.append(row)
+    return out
+
+
+def fm_index_generate(model, index: FMIndex, input_ids, attention_mask, min_length: int = 3, max_length: int = 25,
+                      length_penalty: float = 1.0, num_beams: int = 3, diverse_bs_groups: int = 1,
+                      diverse_bs_penalty: float = 0.0, eos_token_id: Optional[int] = None,
+                      force_decoding_from: Optional[List[int]] = None, always_allow_eos: bool = False,
+                      keep_history: bool = False, disable_fm_index: bool = False, sample: bool = False,
+                      stop_at_count: int = 0, topk: int = 0, transformers_output: bool = False, **kwargs):
+    """beam_search.py:391-557.  `model` is an HF BartForConditionalGeneration (its weights are
+    mirrored on the GPU once and cached) or a SealBartEngine."""
+    if not keep_history:
+        raise NotImplementedError("seal_b200 implements the keep_history=True path SEALSearcher uses "
+                                  "(seal/retrieval.py:70-83,162-176,223-236)")
+    if diverse_bs_groups != 1 or sample or topk or transformers_output:
+        raise NotImplementedError("diverse beam groups / sampling / top-k warping / HF output objects are outside "
+                                  "the constrained-decoding hot path")
+    forced_bos = kwargs.pop("forced_bos_token_id", "config")                     # :415-418
+    rec = generate_records(model, index, input_ids, attention_mask, min_length, max_length, length_penalty,
+                           num_beams, eos_token_id, force_decoding_from, always_allow_eos, disable_fm_index,
+                           stop_at_count, forced_bos, want_ranges=False)
+    return records_to_output(rec, length_penalty)

@@ -1,0 +1,22 @@
+"""`seal_b200.compat.install()` registers this package under the reference's module names so that
+unmodified SEAL callers (`from seal.index import FMIndex`, `from seal.beam_search import
+fm_index_generate`, `from seal.cpp_modules.fm_index import load_FMIndex`) resolve to the B200 path.
+See INTEGRATION.md."""
+import sys
+import types
+
+
+def install():
+    from . import index, beam_search
+    from .cpp_modules import fm_index
+    import seal_b200.cpp_modules as cppm
+    seal = sys.modules.get("seal") or types.ModuleType("seal")
+    seal.FMIndex = index.FMIndex
+    seal.fm_index_generate = beam_search.fm_index_generate
+    seal.IndexBasedLogitsProcessor = beam_search.IndexBasedLogitsProcessor
+    sys.modules["seal"] = seal
+    sys.modules["seal.index"] = index
+    sys.modules["seal.beam_search"] = beam_search
+    sys.modules["seal.cpp_modules"] = cppm
+    sys.modules["seal.cpp_modules.fm_index"] = fm_index
+    return seal

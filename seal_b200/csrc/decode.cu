@@ -1,0 +1,603 @@
+// Host orchestration + C ABI (include/sealdec.h) of the constrained beam-search decode:
+// BART weights, workspace, encoder pass, per-step decoder forward, fused select step.
+#include "../../include/sealdec.h"
+#include "bart_kernels.cuh"
+#include "common.cuh"
+#include "decode_kernels.cuh"
+#include "fm_handle.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+using namespace sealb200;
+
+namespace {
+
+struct Lin { float* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct LNp { float* g = nullptr; float* b = nullptr; };
+struct EncLayerW { Lin qkv, o, fc1, fc2; LNp ln_attn, ln_final; };
+struct DecLayerW { Lin qkv, o, cq, ckv, co, fc1, fc2; LNp ln_self, ln_cross, ln_final; };
+
+struct Buf {
+    void* p = nullptr; size_t bytes = 0;
+    void ensure(size_t need) {
+        if (need <= bytes) return;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        CUDA_CHECK(cudaMalloc(&p, need));
+        bytes = need;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct sealbart {
+    sealbart_config_t cfg{};
+    int device = 0;
+    float* shared = nullptr; float* enc_pos = nullptr; float* dec_pos = nullptr;
+    float* lm_head = nullptr; float* final_bias = nullptr;
+    bool lm_head_given = false;
+    LNp enc_ln_emb, dec_ln_emb;
+    std::vector<EncLayerW> enc;
+    std::vector<DecLayerW> dec;
+    struct Slot { float* dst; uint64_t numel; };
+    std::map<std::string, Slot> slots;
+    std::set<std::string> loaded;
+    std::vector<void*> allocs;
+    uint64_t weight_bytes = 0;
+    bool finalized = false;
+    // workspace
+    Buf enc_tok, enc_mask, ex, eqkv, eattn, etmp, effn, ckv;
+    Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
+    Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
+    Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms;
+    int64_t launches = 0;
+    double phase_us[5] = {0, 0, 0, 0, 0};
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+float* dalloc(sealbart* m, uint64_t numel) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, std::max<uint64_t>(numel, 1) * sizeof(float)));
+    CUDA_CHECK(cudaMemset(p, 0, std::max<uint64_t>(numel, 1) * sizeof(float)));
+    m->allocs.push_back(p);
+    m->weight_bytes += numel * sizeof(float);
+    return static_cast<float*>(p);
+}
+
+void make_lin(sealbart* m, Lin& l, int out, int in) { l.out = out; l.in = in; l.w = dalloc(m, (uint64_t)out * in); l.b = dalloc(m, out); }
+void make_ln(sealbart* m, LNp& l, int d) { l.g = dalloc(m, d); l.b = dalloc(m, d); }
+
+void reg(sealbart* m, const std::string& key, float* dst, uint64_t numel) { m->slots[key] = {dst, numel}; }
+void reg_lin(sealbart* m, const std::string& prefix, Lin& l, int row0, int rows) {
+    reg(m, prefix + ".weight", l.w + (uint64_t)row0 * l.in, (uint64_t)rows * l.in);
+    reg(m, prefix + ".bias", l.b + row0, rows);
+}
+void reg_ln(sealbart* m, const std::string& prefix, LNp& l, int d) {
+    reg(m, prefix + ".weight", l.g, d);
+    reg(m, prefix + ".bias", l.b, d);
+}
+
+void build_slots(sealbart* m) {
+    const auto& c = m->cfg;
+    const int d = c.d_model, f = c.ffn_dim, V = c.vocab_size, P = c.max_positions + 2;
+    m->shared = dalloc(m, (uint64_t)V * d); reg(m, "model.shared.weight", m->shared, (uint64_t)V * d);
+    m->enc_pos = dalloc(m, (uint64_t)P * d); reg(m, "model.encoder.embed_positions.weight", m->enc_pos, (uint64_t)P * d);
+    m->dec_pos = dalloc(m, (uint64_t)P * d); reg(m, "model.decoder.embed_positions.weight", m->dec_pos, (uint64_t)P * d);
+    m->final_bias = dalloc(m, V); reg(m, "final_logits_bias", m->final_bias, V);
+    make_ln(m, m->enc_ln_emb, d); reg_ln(m, "model.encoder.layernorm_embedding", m->enc_ln_emb, d);
+    make_ln(m, m->dec_ln_emb, d); reg_ln(m, "model.decoder.layernorm_embedding", m->dec_ln_emb, d);
+    m->enc.resize(c.encoder_layers);
+    for (int i = 0; i < c.encoder_layers; ++i) {
+        EncLayerW& L = m->enc[i];
+        const std::string p = "model.encoder.layers." + std::to_string(i) + ".";
+        make_lin(m, L.qkv, 3 * d, d);
+        reg_lin(m, p + "self_attn.q_proj", L.qkv, 0, d); reg_lin(m, p + "self_attn.k_proj", L.qkv, d, d);
+        reg_lin(m, p + "self_attn.v_proj", L.qkv, 2 * d, d);
+        make_lin(m, L.o, d, d); reg_lin(m, p + "self_attn.out_proj", L.o, 0, d);
+        make_ln(m, L.ln_attn, d); reg_ln(m, p + "self_attn_layer_norm", L.ln_attn, d);
+        make_lin(m, L.fc1, f, d); reg_lin(m, p + "fc1", L.fc1, 0, f);
+        make_lin(m, L.fc2, d, f); reg_lin(m, p + "fc2", L.fc2, 0, d);
+        make_ln(m, L.ln_final, d); reg_ln(m, p + "final_layer_norm", L.ln_final, d);
+    }
+    m->dec.resize(c.decoder_layers);
+    for (int i = 0; i < c.decoder_layers; ++i) {
+        DecLayerW& L = m->dec[i];
+        const std::string p = "model.decoder.layers." + std::to_string(i) + ".";
+        make_lin(m, L.qkv, 3 * d, d);
+        reg_lin(m, p + "self_attn.q_proj", L.qkv, 0, d); reg_lin(m, p + "self_attn.k_proj", L.qkv, d, d);
+        reg_lin(m, p + "self_attn.v_proj", L.qkv, 2 * d, d);
+        make_lin(m, L.o, d, d); reg_lin(m, p + "self_attn.out_proj", L.o, 0, d);
+        make_ln(m, L.ln_self, d); reg_ln(m, p + "self_attn_layer_norm", L.ln_self, d);
+        make_lin(m, L.cq, d, d); reg_lin(m, p + "encoder_attn.q_proj", L.cq, 0, d);
+        make_lin(m, L.ckv, 2 * d, d);
+        reg_lin(m, p + "encoder_attn.k_proj", L.ckv, 0, d); reg_lin(m, p + "encoder_attn.v_proj", L.ckv, d, d);
+        make_lin(m, L.co, d, d); reg_lin(m, p + "encoder_attn.out_proj", L.co, 0, d);
+        make_ln(m, L.ln_cross, d); reg_ln(m, p + "encoder_attn_layer_norm", L.ln_cross, d);
+        make_lin(m, L.fc1, f, d); reg_lin(m, p + "fc1", L.fc1, 0, f);
+        make_lin(m, L.fc2, d, f); reg_lin(m, p + "fc2", L.fc2, 0, d);
+        make_ln(m, L.ln_final, d); reg_ln(m, p + "final_layer_norm", L.ln_final, d);
+    }
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------
+struct Ctx { sealbart* m; cudaStream_t s; };
+
+void gemm(Ctx& cx, int64_t M, int N, int K, const float* A, int lda, const Lin& l, float* C, int ldc, bool gelu,
+          const float* bias_override = nullptr, const float* w_override = nullptr) {
+    if (M == 0) return;
+    if (K % GBK) throw ApiError(SEALFM_EINVAL, "GEMM K must be a multiple of 16");
+    const float* W = w_override ? w_override : l.w;
+    const float* bias = bias_override ? bias_override : l.b;
+    dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
+    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, W, K, bias, C, ldc);
+    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, W, K, bias, C, ldc);
+    CUDA_CHECK(cudaGetLastError());
+    cx.m->launches++;
+}
+
+void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, float* out) {
+    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out);
+    CUDA_CHECK(cudaGetLastError());
+    cx.m->launches++;
+}
+
+__global__ void prep_enc_kernel(int64_t n, int S, const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                                int32_t* __restrict__ tok, int32_t* __restrict__ m32, int32_t* __restrict__ pos) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    tok[i] = (int32_t)ids[i];
+    m32[i] = mask[i] != 0;
+    pos[i] = (int32_t)(i % S);
+}
+
+__global__ void init_state_kernel(int64_t R, int B, int T, int start_tok, int pad, uint64_t lo0, uint64_t hi0,
+                                  float* __restrict__ scores, int32_t* __restrict__ tokens, uint64_t* __restrict__ lo,
+                                  uint64_t* __restrict__ hi, uint64_t* __restrict__ pw, int32_t* __restrict__ anc) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    scores[r] = (r % B) == 0 ? 0.f : -1e9f;                 // seal/beam_search.py:214-216
+    for (int t = 0; t < T; ++t) { tokens[r * T + t] = t == 0 ? start_tok : pad; anc[r * T + t] = (int32_t)r; }
+    lo[r] = lo0; hi[r] = hi0; pw[r] = hi0 - lo0;
+}
+
+__global__ void ids_to_tokens_kernel(int64_t R, int t, int T, const int64_t* __restrict__ ids, int32_t* __restrict__ tokens,
+                                     int32_t* __restrict__ anc) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    for (int i = 0; i < T; ++i) { tokens[r * T + i] = i < t ? (int32_t)ids[r * t + i] : 0; anc[r * T + i] = (int32_t)r; }
+}
+
+struct Dims { int64_t Q, S, R; int B, T, d, f, V, ld, W; };
+
+void ensure_workspace(sealbart* m, const Dims& D) {
+    const int64_t Tk = D.Q * D.S;
+    const int Ld = m->cfg.decoder_layers;
+    m->enc_tok.ensure(Tk * 4 * 2); m->enc_mask.ensure(Tk * 4);
+    m->ex.ensure(Tk * D.d * 4); m->eqkv.ensure(Tk * 3 * D.d * 4); m->eattn.ensure(Tk * D.d * 4);
+    m->etmp.ensure(Tk * D.d * 4); m->effn.ensure(Tk * D.f * 4);
+    m->ckv.ensure((size_t)Ld * Tk * 2 * D.d * 4);
+    m->dx.ensure(D.R * D.d * 4); m->dqkv.ensure(D.R * 3 * D.d * 4); m->dattn.ensure(D.R * D.d * 4);
+    m->dtmp.ensure(D.R * D.d * 4); m->dcq.ensure(D.R * D.d * 4); m->dffn.ensure(D.R * D.f * 4);
+    m->logits.ensure((size_t)D.R * D.ld * 4);
+    m->kc.ensure((size_t)Ld * D.T * D.R * D.d * 4); m->vc.ensure((size_t)Ld * D.T * D.R * D.d * 4);
+    m->st_scores.ensure(2 * D.R * 4); m->st_tokens.ensure(2 * D.R * D.T * 4);
+    m->st_lo.ensure(2 * D.R * 8); m->st_hi.ensure(2 * D.R * 8); m->st_pw.ensure(2 * D.R * 8);
+    m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
+    m->err.ensure(4);
+}
+
+void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t* mask_d) {
+    sealbart* m = cx.m;
+    const int64_t Tk = D.Q * D.S;
+    const int d = D.d;
+    int32_t* tok = m->enc_tok.as<int32_t>(); int32_t* pos = tok + Tk; int32_t* m32 = m->enc_mask.as<int32_t>();
+    prep_enc_kernel<<<(unsigned)((Tk + 255) / 256), 256, 0, cx.s>>>(Tk, (int)D.S, ids_d, mask_d, tok, m32, pos);
+    CUDA_CHECK(cudaGetLastError()); m->launches++;
+    float* x = m->ex.as<float>(); float* qkv = m->eqkv.as<float>(); float* attn = m->eattn.as<float>();
+    float* tmp = m->etmp.as<float>(); float* ffn = m->effn.as<float>();
+    const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
+    embed_ln_kernel<<<(unsigned)((Tk + 3) / 4), 128, 0, cx.s>>>(Tk, d, tok, 1, pos, 0, m->shared, scale, m->enc_pos,
+                                                                m->enc_ln_emb.g, m->enc_ln_emb.b, x);
+    CUDA_CHECK(cudaGetLastError()); m->launches++;
+    const int heads = m->cfg.heads;
+    for (auto& L : m->enc) {
+        gemm(cx, Tk, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
+        enc_self_attn_kernel<<<(unsigned)Tk, 32 * std::min(heads, 16), 0, cx.s>>>(Tk, d, heads, (int)D.S, qkv, m32, attn);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        gemm(cx, Tk, d, d, attn, d, L.o, tmp, d, false);
+        add_ln(cx, Tk, d, x, tmp, L.ln_attn, x);
+        gemm(cx, Tk, D.f, d, x, d, L.fc1, ffn, D.f, true);
+        gemm(cx, Tk, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
+        add_ln(cx, Tk, d, x, tmp, L.ln_final, x);
+    }
+    // per-query cross-attention K/V of every decoder layer, once (the reference recomputes nothing
+    // either: HF caches them after the first step)
+    for (int l = 0; l < m->cfg.decoder_layers; ++l)
+        gemm(cx, Tk, 2 * d, d, x, d, m->dec[l].ckv, m->ckv.as<float>() + (size_t)l * Tk * 2 * d, 2 * d, false);
+}
+
+// one decoder step for all R rows: token at position pos = cur_len-1 -> logits [R][ld]
+void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, const int32_t* anc, bool want_logits,
+                  cudaEvent_t ev_layers_done) {
+    sealbart* m = cx.m;
+    const int d = D.d; const int64_t R = D.R; const int64_t Tk = D.Q * D.S;
+    const int pos = cur_len - 1;
+    float* x = m->dx.as<float>(); float* qkv = m->dqkv.as<float>(); float* attn = m->dattn.as<float>();
+    float* tmp = m->dtmp.as<float>(); float* cq = m->dcq.as<float>(); float* ffn = m->dffn.as<float>();
+    const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
+    embed_ln_kernel<<<(unsigned)((R + 3) / 4), 128, 0, cx.s>>>(R, d, tokens + pos, D.T, nullptr, pos, m->shared, scale,
+                                                               m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x);
+    CUDA_CHECK(cudaGetLastError()); m->launches++;
+    const int heads = m->cfg.heads;
+    const int32_t* m32 = m->enc_mask.as<int32_t>();
+    for (int l = 0; l < m->cfg.decoder_layers; ++l) {
+        DecLayerW& L = m->dec[l];
+        float* kc = m->kc.as<float>() + (size_t)l * D.T * R * d;
+        float* vc = m->vc.as<float>() + (size_t)l * D.T * R * d;
+        gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
+        dec_self_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv, kc, vc, anc, attn);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
+        add_ln(cx, R, d, x, tmp, L.ln_self, x);
+        gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
+        cross_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, D.B, (int)D.S, cq,
+                                                                            m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32, attn);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
+        add_ln(cx, R, d, x, tmp, L.ln_cross, x);
+        gemm(cx, R, D.f, d, x, d, L.fc1, ffn, D.f, true);
+        gemm(cx, R, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
+        add_ln(cx, R, d, x, tmp, L.ln_final, x);
+    }
+    if (ev_layers_done) CUDA_CHECK(cudaEventRecord(ev_layers_done, cx.s));
+    if (want_logits) {
+        Lin head; head.w = m->lm_head; head.b = m->final_bias; head.out = D.V; head.in = d;
+        gemm(cx, R, D.V, d, x, d, head, m->logits.as<float>(), D.ld, false);
+    }
+}
+
+void check_model(const sealbart* m) {
+    if (!m) throw ApiError(SEALFM_EINVAL, "null model");
+    if (!m->finalized) throw ApiError(SEALFM_EINVAL, "sealbart_finalize not called");
+    CUDA_CHECK(cudaSetDevice(m->device));
+}
+
+Dims make_dims(const sealbart* m, int64_t Q, int64_t S, int B, int T) {
+    Dims D;
+    D.Q = Q; D.S = S; D.B = B; D.R = Q * B; D.T = T;
+    D.d = m->cfg.d_model; D.f = m->cfg.ffn_dim; D.V = m->cfg.vocab_size;
+    D.ld = (D.V + 3) / 4 * 4; D.W = (D.V + 31) / 32;
+    return D;
+}
+
+cudaEvent_t new_event(sealbart* m) {
+    cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); m->events.push_back(e); return e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sealbart_create(const sealbart_config_t* cfg, int device, sealbart_t** out) {
+    return guarded([&] {
+        if (!cfg || !out) throw ApiError(SEALFM_EINVAL, "null argument");
+        if (cfg->d_model % 128 || cfg->d_model > 1024 || cfg->heads * kHeadDim != cfg->d_model)
+            throw ApiError(SEALFM_EINVAL, "d_model must be a multiple of 128, <= 1024, with 64-wide heads");
+        if (cfg->ffn_dim % 16 || cfg->vocab_size <= 0) throw ApiError(SEALFM_EINVAL, "bad ffn_dim / vocab_size");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0) { cudaGetLastError(); throw ApiError(SEALFM_ENODEVICE, "no CUDA device available"); }
+        if (device < 0 || device >= count) throw ApiError(SEALFM_EINVAL, "bad device id");
+        CUDA_CHECK(cudaSetDevice(device));
+        std::unique_ptr<sealbart> m(new sealbart());
+        m->cfg = *cfg; m->device = device;
+        build_slots(m.get());
+        *out = m.release();
+    });
+}
+
+void sealbart_free(sealbart_t* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    for (void* p : m->allocs) cudaFree(p);
+    if (m->lm_head_given) cudaFree(m->lm_head);
+    for (Buf* b : {&m->enc_tok, &m->enc_mask, &m->ex, &m->eqkv, &m->eattn, &m->etmp, &m->effn, &m->ckv, &m->dx, &m->dqkv,
+                   &m->dattn, &m->dtmp, &m->dcq, &m->dffn, &m->logits, &m->kc, &m->vc, &m->st_scores, &m->st_tokens,
+                   &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->hy_score, &m->hy_len, &m->hy_tok,
+                   &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms})
+        b->release();
+    for (auto e : m->events) cudaEventDestroy(e);
+    delete m;
+}
+
+int sealbart_set_tensor(sealbart_t* m, const char* key, const float* host, uint64_t numel) {
+    return guarded([&] {
+        if (!m || !key || !host) throw ApiError(SEALFM_EINVAL, "null argument");
+        CUDA_CHECK(cudaSetDevice(m->device));
+        std::string k(key);
+        if (k == "lm_head.weight") {
+            const uint64_t want = (uint64_t)m->cfg.vocab_size * m->cfg.d_model;
+            if (numel != want) throw ApiError(SEALFM_EINVAL, "lm_head.weight: wrong size");
+            if (!m->lm_head_given) { CUDA_CHECK(cudaMalloc(&m->lm_head, want * 4)); m->lm_head_given = true; m->weight_bytes += want * 4; }
+            CUDA_CHECK(cudaMemcpy(m->lm_head, host, want * 4, cudaMemcpyHostToDevice));
+            return;
+        }
+        if (k == "model.encoder.embed_tokens.weight" || k == "model.decoder.embed_tokens.weight") k = "model.shared.weight";
+        auto it = m->slots.find(k);
+        if (it == m->slots.end()) throw ApiError(SEALFM_EINVAL, "unknown state_dict key: " + k);
+        if (it->second.numel != numel) throw ApiError(SEALFM_EINVAL, "wrong element count for " + k);
+        CUDA_CHECK(cudaMemcpy(it->second.dst, host, numel * 4, cudaMemcpyHostToDevice));
+        m->loaded.insert(k);
+        m->finalized = false;
+    });
+}
+
+int sealbart_finalize(sealbart_t* m) {
+    return guarded([&] {
+        if (!m) throw ApiError(SEALFM_EINVAL, "null model");
+        for (auto& kv : m->slots)
+            if (!m->loaded.count(kv.first)) throw ApiError(SEALFM_EINVAL, "state_dict tensor missing: " + kv.first);
+        if (!m->lm_head_given) m->lm_head = m->shared;          // tied (seal/utils.py:48-49)
+        m->finalized = true;
+    });
+}
+
+uint64_t sealbart_device_bytes(const sealbart_t* m) { return m ? m->weight_bytes : 0; }
+
+int64_t sealdec_hyps_per_query(const sealdec_params_t* p) {
+    if (!p) return 0;
+    return (int64_t)(p->max_length - 1) * 2 * p->num_beams + p->num_beams;
+}
+
+int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d, const sealdec_params_t* p,
+                       const int64_t* ids_d, const int64_t* mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
+                       float* o_score, int32_t* o_len, int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo,
+                       uint64_t* o_hi, int32_t* err_d) {
+    return guarded([&] {
+        check_model(m);
+        if (!p || !ids_d || !mask_d || !o_score || !o_len || !o_tok || !o_valid) throw ApiError(SEALFM_EINVAL, "null argument");
+        const int B = p->num_beams, K = 2 * B, T = p->max_length;
+        if (B < 1 || B > kSelMaxBeams || K > kSelMaxK) throw ApiError(SEALFM_EINVAL, "num_beams must be in [1,32]");
+        if (T < 2 || T > kMaxLen) throw ApiError(SEALFM_EINVAL, "max_length must be in [2,32]");
+        if (Q <= 0 || S <= 0) throw ApiError(SEALFM_EINVAL, "empty batch");
+        if (S > m->cfg.max_positions) throw ApiError(SEALFM_EINVAL, "source longer than max_positions");
+        FmView view{};
+        uint64_t lo0 = 0, hi0 = 0;
+        if (!p->disable_fm_index) {
+            if (!fm || sealfm_device(fm) != m->device) throw ApiError(SEALFM_ENODEVICE, "FM index not bound to the model's device");
+            if (!occ_d) throw ApiError(SEALFM_EINVAL, "occurring mask missing");
+            view = sealfm_view(fm);
+            lo0 = 0; hi0 = view.m + 1;                               // get_range([]) = (0, size()+1)  (index.py:106-110)
+            if (p->n_force_decoding_from > 0) {
+                std::vector<uint64_t> q(p->n_force_decoding_from), off{0, (uint64_t)p->n_force_decoding_from};
+                for (int i = 0; i < p->n_force_decoding_from; ++i) q[i] = (uint64_t)p->force_decoding_from[i] + p->shift;
+                int rc = sealfm_backward_search_multi(fm, 1, q.data(), off.data(), &lo0, &hi0);
+                if (rc) throw ApiError(rc, sealfm_last_error());
+            }
+        }
+        Ctx cx{m, (cudaStream_t)stream};
+        m->launches = 0;
+        const Dims D = make_dims(m, Q, S, B, T);
+        ensure_workspace(m, D);
+        for (auto e : m->events) cudaEventDestroy(e);
+        m->events.clear();
+        cudaEvent_t ev0 = new_event(m), ev_enc = new_event(m);
+        CUDA_CHECK(cudaEventRecord(ev0, cx.s));
+        encoder_forward(cx, D, ids_d, mask_d);
+        CUDA_CHECK(cudaEventRecord(ev_enc, cx.s));
+
+        const int64_t R = D.R;
+        float* sc[2] = {m->st_scores.as<float>(), m->st_scores.as<float>() + R};
+        int32_t* tk[2] = {m->st_tokens.as<int32_t>(), m->st_tokens.as<int32_t>() + R * T};
+        uint64_t* lo[2] = {m->st_lo.as<uint64_t>(), m->st_lo.as<uint64_t>() + R};
+        uint64_t* hi[2] = {m->st_hi.as<uint64_t>(), m->st_hi.as<uint64_t>() + R};
+        uint64_t* pw[2] = {m->st_pw.as<uint64_t>(), m->st_pw.as<uint64_t>() + R};
+        int32_t* an[2] = {m->st_anc.as<int32_t>(), m->st_anc.as<int32_t>() + R * T};
+        uint32_t* mk[2] = {m->st_mask.as<uint32_t>(), m->st_mask.as<uint32_t>() + (size_t)R * D.W};
+        init_state_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(R, B, T, p->decoder_start_token_id, p->pad_token_id,
+                                                                        lo0, hi0, sc[0], tk[0], lo[0], hi[0], pw[0], an[0]);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        CUDA_CHECK(cudaMemsetAsync(err_d, 0, 4, cx.s));
+
+        StepCfg c{};
+        c.num_beams = B; c.K = K; c.V = D.V; c.ld = D.ld;
+        c.min_length = p->min_length; c.max_length = p->max_length;
+        c.eos_token_id = p->eos_token_id; c.pad_token_id = p->pad_token_id; c.model_eos_token_id = p->model_eos_token_id;
+        c.forced_eos_token_id = p->forced_eos_token_id; c.forced_bos_token_id = p->forced_bos_token_id;
+        c.stop_at_count = p->stop_at_count; c.always_allow_eos = p->always_allow_eos; c.disable_fm_index = p->disable_fm_index;
+        c.remove_invalid_values = p->remove_invalid_values; c.shift = p->shift; c.T = T; c.mask_words = D.W;
+        c.hyps_per_query = sealdec_hyps_per_query(p);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+            attr_set = true;
+        }
+        std::vector<cudaEvent_t> ev_a, ev_b, ev_c, ev_d;
+        int cur = 0;
+        for (int step = 0; step + 1 < T; ++step) {
+            const int cur_len = step + 1;
+            cudaEvent_t a = new_event(m), b = new_event(m), cc = new_event(m), dd = new_event(m);
+            CUDA_CHECK(cudaEventRecord(a, cx.s));
+            decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b);
+            CUDA_CHECK(cudaEventRecord(cc, cx.s));
+            c.cur_len = cur_len;
+            const int eff_len = cur_len - (p->forced_bos_token_id >= 0 ? 1 : 0);
+            c.first_step_shared_mask = (!p->disable_fm_index && eff_len == 1) ? 1 : 0;
+            c.expand_next = (cur_len + 1 < T) ? 1 : 0;
+            c.hyp_base = step * K;
+            StepState st{};
+            st.beam_scores_in = sc[cur]; st.beam_scores_out = sc[cur ^ 1];
+            st.tokens_in = tk[cur]; st.tokens_out = tk[cur ^ 1];
+            st.lo_in = lo[cur]; st.lo_out = lo[cur ^ 1]; st.hi_in = hi[cur]; st.hi_out = hi[cur ^ 1];
+            st.pw_in = pw[cur]; st.pw_out = pw[cur ^ 1];
+            st.anc_in = an[cur]; st.anc_out = an[cur ^ 1];
+            st.mask_in = mk[cur]; st.mask_out = mk[cur ^ 1];
+            st.occurring_mask = occ_d; st.logits = m->logits.as<float>();
+            st.hyp_score = o_score; st.hyp_len = o_len; st.hyp_tokens = o_tok; st.hyp_valid = o_valid;
+            st.hyp_lo = o_lo; st.hyp_hi = o_hi; st.error_flag = err_d;
+            select_step_kernel<0><<<(unsigned)Q, kSelThreads, sizeof(SelShared), cx.s>>>(view, c, st);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            CUDA_CHECK(cudaEventRecord(dd, cx.s));
+            ev_a.push_back(a); ev_b.push_back(b); ev_c.push_back(cc); ev_d.push_back(dd);
+            cur ^= 1;
+        }
+        c.cur_len = T; c.hyp_base = (T - 1) * K;
+        StepState st{};
+        st.hyp_score = o_score; st.hyp_len = o_len; st.hyp_tokens = o_tok; st.hyp_valid = o_valid; st.hyp_lo = o_lo; st.hyp_hi = o_hi;
+        finalize_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(Q, c, sc[cur], tk[cur], lo[cur], hi[cur], st);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        cudaEvent_t ev_end = new_event(m);
+        CUDA_CHECK(cudaEventRecord(ev_end, cx.s));
+        // phase accounting is resolved lazily in sealdec_last_phase_us (needs the stream to drain)
+        m->phase_us[0] = -1;
+        // stash event handles in order: ev0, ev_enc, then per step a,b,c,d, then end
+        // (m->events already holds them in creation order)
+    });
+}
+
+int sealdec_last_phase_us(const sealbart_t* mc, double out5[5]) {
+    return guarded([&] {
+        sealbart* m = const_cast<sealbart*>(mc);
+        if (!m || !out5) throw ApiError(SEALFM_EINVAL, "null argument");
+        CUDA_CHECK(cudaSetDevice(m->device));
+        const size_t n = m->events.size();
+        if (n < 3) throw ApiError(SEALFM_EINVAL, "no generate call recorded");
+        CUDA_CHECK(cudaEventSynchronize(m->events[n - 1]));
+        auto ms = [&](size_t a, size_t b) { float t = 0; CUDA_CHECK(cudaEventElapsedTime(&t, m->events[a], m->events[b])); return (double)t * 1e3; };
+        double enc = ms(0, 1), layers = 0, head = 0, sel = 0;
+        for (size_t i = 2; i + 3 < n; i += 4) { layers += ms(i, i + 1); head += ms(i + 1, i + 2); sel += ms(i + 2, i + 3); }
+        out5[0] = enc; out5[1] = layers; out5[2] = head; out5[3] = sel; out5[4] = ms(0, n - 1);
+    });
+}
+
+int64_t sealdec_last_launch_count(const sealbart_t* m) { return m ? m->launches : 0; }
+
+int sealdec_generate(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_host, const sealdec_params_t* p,
+                     const int64_t* ids, const int64_t* mask, int64_t Q, int64_t S, float* o_score, int32_t* o_len,
+                     int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo, uint64_t* o_hi) {
+    return guarded([&] {
+        check_model(m);
+        if (!p || !ids || !mask) throw ApiError(SEALFM_EINVAL, "null argument");
+        const int64_t H = sealdec_hyps_per_query(p), T = p->max_length;
+        const int W = (m->cfg.vocab_size + 31) / 32;
+        Buf d_ids, d_mask, d_occ;
+        d_ids.ensure(Q * S * 8); d_mask.ensure(Q * S * 8); d_occ.ensure((size_t)W * 4);
+        struct Rel { Buf *a, *b, *c; ~Rel() { a->release(); b->release(); c->release(); } } rel{&d_ids, &d_mask, &d_occ};
+        cudaStream_t s = nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(d_ids.p, ids, Q * S * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(d_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
+        if (occ_host) CUDA_CHECK(cudaMemcpyAsync(d_occ.p, occ_host, (size_t)W * 4, cudaMemcpyHostToDevice, s));
+        m->hy_score.ensure(Q * H * 4); m->hy_len.ensure(Q * H * 4); m->hy_tok.ensure(Q * H * T * 4);
+        m->hy_valid.ensure(Q * H); m->hy_lo.ensure(Q * H * 8); m->hy_hi.ensure(Q * H * 8); m->err.ensure(4);
+        int rc = sealdec_generate_d(m, fm, occ_host ? d_occ.as<uint32_t>() : nullptr, p, d_ids.as<int64_t>(), d_mask.as<int64_t>(),
+                                    Q, S, s, m->hy_score.as<float>(), m->hy_len.as<int32_t>(), m->hy_tok.as<int32_t>(),
+                                    m->hy_valid.as<uint8_t>(), o_lo ? m->hy_lo.as<uint64_t>() : nullptr,
+                                    o_hi ? m->hy_hi.as<uint64_t>() : nullptr, m->err.as<int32_t>());
+        if (rc) throw ApiError(rc, last_error());
+        CUDA_CHECK(cudaMemcpyAsync(o_score, m->hy_score.p, Q * H * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(o_len, m->hy_len.p, Q * H * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(o_tok, m->hy_tok.p, Q * H * T * 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(o_valid, m->hy_valid.p, Q * H, cudaMemcpyDeviceToHost, s));
+        if (o_lo) CUDA_CHECK(cudaMemcpyAsync(o_lo, m->hy_lo.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
+        if (o_hi) CUDA_CHECK(cudaMemcpyAsync(o_hi, m->hy_hi.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
+        int32_t err = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&err, m->err.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (err) throw ApiError(SEALFM_EINVAL, "beam: fewer than num_beams non-EOS candidates (seal/beam_search.py:687-690)");
+    });
+}
+
+int sealdec_debug_step_logits(sealbart_t* m, const int64_t* ids, const int64_t* mask, int64_t Q, int64_t S, int32_t B,
+                              const int64_t* dec_ids, int64_t t, float* out_logits) {
+    return guarded([&] {
+        check_model(m);
+        if (!ids || !mask || !dec_ids || !out_logits || t < 1 || t > kMaxLen) throw ApiError(SEALFM_EINVAL, "bad argument");
+        const int T = (int)t;
+        const Dims D = make_dims(m, Q, S, B, T);
+        ensure_workspace(m, D);
+        Buf d_ids, d_mask;
+        d_ids.ensure(Q * S * 8); d_mask.ensure(Q * S * 8); m->dbg_ids.ensure(D.R * t * 8);
+        struct Rel { Buf *a, *b; ~Rel() { a->release(); b->release(); } } rel{&d_ids, &d_mask};
+        cudaStream_t s = nullptr;
+        CUDA_CHECK(cudaMemcpyAsync(d_ids.p, ids, Q * S * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(d_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(m->dbg_ids.p, dec_ids, D.R * t * 8, cudaMemcpyHostToDevice, s));
+        Ctx cx{m, s};
+        m->launches = 0;
+        encoder_forward(cx, D, d_ids.as<int64_t>(), d_mask.as<int64_t>());
+        int32_t* tk = m->st_tokens.as<int32_t>(); int32_t* an = m->st_anc.as<int32_t>();
+        ids_to_tokens_kernel<<<(unsigned)((D.R + 255) / 256), 256, 0, s>>>(D.R, T, T, m->dbg_ids.as<int64_t>(), tk, an);
+        CUDA_CHECK(cudaGetLastError());
+        for (int cur_len = 1; cur_len <= T; ++cur_len) decoder_step(cx, D, tk, cur_len, an, cur_len == T, nullptr);
+        CUDA_CHECK(cudaMemcpy2DAsync(out_logits, (size_t)D.V * 4, m->logits.p, (size_t)D.ld * 4, (size_t)D.V * 4, D.R,
+                                     cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int sealdec_apply_index_mask_d(const sealfm_t* fm, sealfm_stream_t stream, const sealdec_processor_cfg_t* cfg,
+                               const int64_t* input_ids_d, int64_t R, int64_t t, const uint32_t* occ_d,
+                               const float* in_d, float* out_d, int64_t V, int64_t ld) {
+    return guarded([&] {
+        if (!fm || !cfg || !input_ids_d || !in_d || !out_d) throw ApiError(SEALFM_EINVAL, "null argument");
+        const int dev = sealfm_device(fm);
+        if (dev < 0) throw ApiError(SEALFM_ENODEVICE, "index not bound to a CUDA device (call sealfm_to_device)");
+        CUDA_CHECK(cudaSetDevice(dev));
+        if (R <= 0 || t < 1) throw ApiError(SEALFM_EINVAL, "empty input");
+        cudaStream_t s = (cudaStream_t)stream;
+        const FmView view = sealfm_view(fm);
+        const int W = (int)((V + 31) / 32);
+        dim3 grid(std::min<int64_t>((V + 255) / 256, 64), (unsigned)R);
+        const bool fb = cfg->forced_bos_token_id >= 0;
+        if (fb && t == 1) {                                                     // :66-69
+            apply_mask_kernel<<<grid, 256, 0, s>>>(R, (int)V, ld, in_d, out_d, nullptr, W, 1, nullptr, cfg->eos_token_id,
+                                                   cfg->pad_token_id, 0, cfg->forced_bos_token_id);
+            CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+        const int skip = fb ? 1 : 0;                                            // :71
+        if (t - skip == 1) {                                                    // :73-77
+            if (!occ_d) throw ApiError(SEALFM_EINVAL, "occurring mask missing");
+            apply_mask_kernel<<<grid, 256, 0, s>>>(R, (int)V, ld, in_d, out_d, occ_d, W, 1, nullptr, cfg->eos_token_id,
+                                                   cfg->pad_token_id, cfg->always_allow_eos, -1);
+            CUDA_CHECK(cudaGetLastError());
+            return;
+        }
+        // scratch: lo, hi (u64), rule (u8), masks — stream-ordered allocation, no host sync
+        uint64_t* lo = nullptr; uint64_t* hi = nullptr; uint8_t* rule = nullptr; uint32_t* masks = nullptr; uint64_t* fsyms = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&lo, R * 8, s)); CUDA_CHECK(cudaMallocAsync(&hi, R * 8, s));
+        CUDA_CHECK(cudaMallocAsync(&rule, R, s)); CUDA_CHECK(cudaMallocAsync(&masks, (size_t)R * W * 4, s));
+        const int nf = cfg->n_force_decoding_from;
+        if (nf > 0) {
+            std::vector<uint64_t> f(nf);
+            for (int i = 0; i < nf; ++i) f[i] = (uint64_t)cfg->force_decoding_from[i] + cfg->shift;
+            CUDA_CHECK(cudaMallocAsync(&fsyms, nf * 8, s));
+            CUDA_CHECK(cudaMemcpyAsync(fsyms, f.data(), nf * 8, cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));   // f is a stack temporary
+        }
+        rows_fold_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(view, R, (int)t, input_ids_d, skip, cfg->eos_token_id,
+                                                                    cfg->pad_token_id, cfg->stop_at_count, fsyms, nf, cfg->shift,
+                                                                    lo, hi, rule);
+        CUDA_CHECK(cudaGetLastError());
+        int rc = sealfm_expand_mask_d(fm, s, R, lo, hi, masks, W, (uint32_t)V, (uint32_t)cfg->shift);
+        if (rc) throw ApiError(rc, sealfm_last_error());
+        apply_mask_kernel<<<grid, 256, 0, s>>>(R, (int)V, ld, in_d, out_d, masks, W, 0, rule, cfg->eos_token_id,
+                                               cfg->pad_token_id, cfg->always_allow_eos, -1);
+        CUDA_CHECK(cudaGetLastError());
+        cudaFreeAsync(lo, s); cudaFreeAsync(hi, s); cudaFreeAsync(rule, s); cudaFreeAsync(masks, s);
+        if (fsyms) cudaFreeAsync(fsyms, s);
+    });
+}
+
+}  // extern "C"

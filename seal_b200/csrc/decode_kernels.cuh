@@ -1,0 +1,422 @@
+// Constrained beam-search step on the device: full-vocabulary log-softmax, HF logits processors,
+// FM-index mask, top-(2*beam) over the constrained scores, BeamSearchScorerWithMemory bookkeeping,
+// LF-mapping of the surviving beams and expansion of their successor sets — ONE kernel per step,
+// one CTA per query.  Replaces seal/beam_search.py:244-332 + :614-703 and the CPU FM-index work of
+// :62-140 without a single host synchronisation.
+#pragma once
+#include "fm_device.cuh"
+#include "fm_expand.cuh"
+
+#include <cfloat>
+#include <cstdint>
+
+namespace sealb200 {
+
+constexpr int kSelThreads = 512;
+constexpr int kSelBuf = 8192;          // candidate staging buffer (entries)
+constexpr int kSelMaxK = 64;           // 2*num_beams <= 64
+constexpr int kSelMaxBeams = 32;
+constexpr int kMaxLen = 32;            // max_length <= 32 (SEAL: 10 body, 15 title)
+
+struct StepCfg {
+    int32_t num_beams, K;              // K = 2*num_beams
+    int32_t V, ld;                     // vocab, logits leading dimension
+    int32_t cur_len;                   // tokens per row so far (t); this step picks token t
+    int32_t min_length, max_length;
+    int32_t eos_token_id, pad_token_id, model_eos_token_id, forced_eos_token_id, forced_bos_token_id;
+    int32_t stop_at_count, always_allow_eos, disable_fm_index, remove_invalid_values;
+    int32_t shift;
+    int32_t T;                         // token row stride (>= max_length)
+    int32_t mask_words;                // words per bitmask row
+    int32_t first_step_shared_mask;    // 1: every row uses occurring_mask (seal/beam_search.py:73-77)
+    int32_t expand_next;               // 0 on the last step
+    int64_t hyps_per_query;
+    int32_t hyp_base;                  // index of this step's first hypothesis record
+};
+
+struct StepState {
+    // per row (R = Q*num_beams), double-buffered by the caller
+    const float* beam_scores_in;  float* beam_scores_out;
+    const int32_t* tokens_in;     int32_t* tokens_out;        // [R][T]
+    const uint64_t* lo_in;        uint64_t* lo_out;           // SA range [lo, hi) of tokens[1:]
+    const uint64_t* hi_in;        uint64_t* hi_out;
+    const uint64_t* pw_in;        uint64_t* pw_out;           // width of the range before the last token
+    const int32_t* anc_in;        int32_t* anc_out;           // [R][T] KV ancestry
+    const uint32_t* mask_in;      uint32_t* mask_out;         // [R][mask_words] allowed-token bitmasks
+    const uint32_t* occurring_mask;                           // [mask_words]
+    const float* logits;                                      // [R][ld]
+    // hypothesis records
+    float* hyp_score; int32_t* hyp_len; int32_t* hyp_tokens; uint8_t* hyp_valid; uint64_t* hyp_lo; uint64_t* hyp_hi;
+    int32_t* error_flag;
+};
+
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) r += red[w];
+    __syncthreads();
+    return r;
+}
+
+// HF-4.13 processors applied to a log-probability (order MinLength -> ForcedBOS ->
+// ForcedEOS -> InfNanRemove), seal/beam_search.py:255.
+__device__ __forceinline__ float apply_processors(const StepCfg& c, int v, float p) {
+    if (c.min_length > -1 && c.cur_len < c.min_length && v == c.model_eos_token_id) p = -INFINITY;
+    if (c.forced_bos_token_id >= 0 && c.cur_len == 1) p = (v == c.forced_bos_token_id) ? 0.f : -INFINITY;
+    if (c.forced_eos_token_id >= 0 && c.cur_len == c.max_length - 1) p = (v == c.forced_eos_token_id) ? 0.f : -INFINITY;
+    if (c.remove_invalid_values) {
+        if (p != p) p = 0.f;
+        if (p == INFINITY) p = FLT_MAX;
+    }
+    return p;
+}
+
+// better(a,b): a precedes b in the top-k order — larger score first, lower flat index on ties.
+__device__ __forceinline__ bool cand_better(float sa, int ia, float sb, int ib) {
+    return sa > sb || (sa == sb && ia < ib);
+}
+
+struct SelShared {
+    float cval[kSelBuf + kSelMaxK];
+    int cidx[kSelBuf + kSelMaxK];
+    float tval[kSelMaxK];
+    int tidx[kSelMaxK];
+    uint8_t tvalid[kSelMaxK];
+    float row_max[kSelMaxBeams], row_logsum[kSelMaxBeams];
+    uint8_t row_rule[kSelMaxBeams];       // 0 index set, 1 only eos, 2 only pad
+    float red[kSelThreads / 32];
+    float rv[kSelThreads / 32]; int ri[kSelThreads / 32]; int rslot[kSelThreads / 32];
+    int ccount, tcount;
+    float thr; int thr_idx;
+    int nbeam_src[kSelMaxBeams];          // candidate index feeding each new beam
+    int n_noneos;
+    WarpFrontier frontier[kSelThreads / 32];
+};
+
+// Select the best min(K, n) of the n staged candidates (cval/cidx[0..n)) in order; result in
+// tval/tidx[0..tcount).  K rounds of block-wide arg-best.
+__device__ void sel_merge(SelShared& S, int K) {
+    // current top list is appended to the staging area so one pass handles both
+    __syncthreads();
+    int n = S.ccount;
+    for (int i = threadIdx.x; i < S.tcount; i += blockDim.x) { S.cval[n + i] = S.tval[i]; S.cidx[n + i] = S.tidx[i]; }
+    __syncthreads();
+    n += S.tcount;
+    const int want = n < K ? n : K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int round = 0; round < want; ++round) {
+        float bv = -INFINITY; int bi = 0x7fffffff; int bs = -1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int id = S.cidx[i];
+            if (id < 0) continue;                        // already taken
+            const float v = S.cval[i];
+            if (bs < 0 || cand_better(v, id, bv, bi)) { bv = v; bi = id; bs = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (os >= 0 && (bs < 0 || cand_better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
+        }
+        if (lane == 0) { S.rv[warp] = bv; S.ri[warp] = bi; S.rslot[warp] = bs; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = S.rv[0]; int id = S.ri[0]; int sl = S.rslot[0];
+            for (int w = 1; w < nw; ++w)
+                if (S.rslot[w] >= 0 && (sl < 0 || cand_better(S.rv[w], S.ri[w], v, id))) { v = S.rv[w]; id = S.ri[w]; sl = S.rslot[w]; }
+            S.tval[round] = v; S.tidx[round] = id;
+            S.cidx[sl] = -1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        S.tcount = want; S.ccount = 0;
+        if (want == K) { S.thr = S.tval[K - 1]; S.thr_idx = S.tidx[K - 1]; }
+    }
+    __syncthreads();
+}
+
+template <int DUMMY = 0>
+__global__ void __launch_bounds__(kSelThreads, 1) select_step_kernel(FmView fm, StepCfg c, StepState st) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SelShared& S = *reinterpret_cast<SelShared*>(smem_raw);
+    const int B = c.num_beams, K = c.K, V = c.V;
+    const int64_t qi = blockIdx.x;
+    const int64_t r0 = qi * B;
+    const int tid = threadIdx.x;
+    if (tid == 0) { S.ccount = 0; S.tcount = 0; S.thr = -INFINITY; S.thr_idx = 0x7fffffff; S.n_noneos = 0; }
+    __syncthreads();
+
+    for (int b = 0; b < B; ++b) {
+        const int64_t r = r0 + b;
+        const float* lp = st.logits + r * c.ld;
+        // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251) --------------------
+        float mx = -INFINITY;
+        for (int v = tid * 4; v < V; v += kSelThreads * 4) {
+            if (v + 3 < V) {
+                const float4 x = *reinterpret_cast<const float4*>(lp + v);
+                mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+            } else {
+                for (int u = v; u < V; ++u) mx = fmaxf(mx, lp[u]);
+            }
+        }
+        mx = block_reduce_max(mx, S.red);
+        float se = 0.f;
+        for (int v = tid * 4; v < V; v += kSelThreads * 4) {
+            if (v + 3 < V) {
+                const float4 x = *reinterpret_cast<const float4*>(lp + v);
+                se += expf(x.x - mx) + expf(x.y - mx) + expf(x.z - mx) + expf(x.w - mx);
+            } else {
+                for (int u = v; u < V; ++u) se += expf(lp[u] - mx);
+            }
+        }
+        se = block_reduce_sum(se, S.red);
+        const float logsum = logf(se);
+        // ---- which tokens does the index allow on this row (seal/beam_search.py:87-135) ----------
+        const int32_t* trow = st.tokens_in + r * c.T;
+        const int last = trow[c.cur_len - 1];
+        int rule = 0;
+        const uint32_t* mrow = c.first_step_shared_mask ? st.occurring_mask : st.mask_in + r * c.mask_words;
+        const bool fm_step = !c.disable_fm_index && !(c.forced_bos_token_id >= 0 && c.cur_len == 1);
+        // with forced_bos the reference drops the first column before looking at lengths (:66-71)
+        const int eff_len = c.cur_len - (c.forced_bos_token_id >= 0 ? 1 : 0);
+        if (fm_step && eff_len > 1) {
+            const bool ended = (last == c.eos_token_id || last == c.pad_token_id);
+            const uint64_t count = ended ? 0 : st.pw_in[r];
+            if (c.stop_at_count > 0 && count <= (uint64_t)c.stop_at_count) rule = 1;
+            else if (ended) rule = 2;
+        }
+        if (tid == 0) { S.row_max[b] = mx; S.row_logsum[b] = logsum; S.row_rule[b] = (uint8_t)rule; }
+        const float bs = st.beam_scores_in[r];
+        // ---- stage candidates whose constrained score is finite and not below the running k-th best
+        for (int w0 = 0; w0 < c.mask_words; w0 += kSelThreads) {
+            const int w = w0 + tid;
+            uint32_t bits = 0;
+            if (w < c.mask_words) {
+                if (c.disable_fm_index) bits = 0xffffffffu;
+                else if (c.forced_bos_token_id >= 0 && c.cur_len == 1) bits = (c.forced_bos_token_id >> 5) == w ? 1u << (c.forced_bos_token_id & 31) : 0u;
+                else if (rule == 1) bits = (c.eos_token_id >> 5) == w ? 1u << (c.eos_token_id & 31) : 0u;
+                else if (rule == 2) bits = (c.pad_token_id >> 5) == w ? 1u << (c.pad_token_id & 31) : 0u;
+                else bits = mrow[w];
+                if (c.always_allow_eos && !c.disable_fm_index && !(c.forced_bos_token_id >= 0 && c.cur_len == 1) &&
+                    (c.eos_token_id >> 5) == w) bits |= 1u << (c.eos_token_id & 31);
+                if (w == c.mask_words - 1 && (V & 31)) bits &= (1u << (V & 31)) - 1;
+            }
+            for (int sub = 0; sub < 4; ++sub) {
+                uint32_t part = (bits >> (8 * sub)) & 0xffu;
+                while (part) {
+                    const int bit = __ffs(part) - 1; part &= part - 1;
+                    const int v = w * 32 + 8 * sub + bit;
+                    float p = (lp[v] - mx) - logsum;
+                    p = apply_processors(c, v, p);
+                    const float s = p + bs;
+                    const int flat = b * V + v;
+                    if (s > -INFINITY && (S.tcount < K || cand_better(s, flat, S.thr, S.thr_idx))) {
+                        const int slot = atomicAdd(&S.ccount, 1);
+                        S.cval[slot] = s; S.cidx[slot] = flat;
+                    }
+                }
+                __syncthreads();
+                const int staged = S.ccount;                                 // read between two barriers:
+                __syncthreads();                                             // the branch below is uniform
+                if (staged > kSelBuf - kSelThreads * 8) sel_merge(S, K);
+            }
+        }
+    }
+    sel_merge(S, K);
+
+    // ---- fewer than K finite constrained candidates: fill with masked ones -------
+    // torch.topk's choice among -inf ties is unspecified; ours: lowest flat index first.
+    if (tid < kSelMaxK) S.tvalid[tid] = tid < S.tcount ? 1 : 0;
+    __syncthreads();
+    if (tid == 0 && S.tcount < K) {
+        int have = S.tcount;
+        for (int flat = 0; have < K && flat < B * V; ++flat) {
+            const int b = flat / V, v = flat - b * V;
+            const int64_t r = r0 + b;
+            float p = (st.logits[r * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
+            p = apply_processors(c, v, p);
+            const float s = p + st.beam_scores_in[r];
+            // was it a finite constrained candidate (then it is already in the list)?
+            bool allowed;
+            if (c.disable_fm_index) allowed = true;
+            else if (c.forced_bos_token_id >= 0 && c.cur_len == 1) allowed = v == c.forced_bos_token_id;
+            else {
+                const uint32_t* mrow = c.first_step_shared_mask ? st.occurring_mask : st.mask_in + r * c.mask_words;
+                const int rule = S.row_rule[b];
+                allowed = rule == 1 ? v == c.eos_token_id : rule == 2 ? v == c.pad_token_id : ((mrow[v >> 5] >> (v & 31)) & 1);
+                if (c.always_allow_eos && v == c.eos_token_id) allowed = true;
+            }
+            if (allowed && s > -INFINITY) continue;
+            S.tval[have] = s; S.tidx[have] = flat; S.tvalid[have] = 0; ++have;
+        }
+        S.tcount = have;
+    }
+    __syncthreads();
+
+    // ---- BeamSearchScorerWithMemory.process (seal/beam_search.py:642-695) -----------------------
+    if (tid == 0) {
+        int nb = 0;
+        for (int k = 0; k < K; ++k) {
+            const int tok = S.tidx[k] % V;
+            if (tok != c.eos_token_id && nb < B) S.nbeam_src[nb++] = k;     // :673-681
+        }
+        S.n_noneos = nb;
+        if (nb < B) atomicExch(st.error_flag, 1);                           // :687-690 ValueError
+    }
+    __syncthreads();
+    const int new_len = c.cur_len + 1;
+    if (tid < K) {
+        const int k = tid;
+        const int flat = S.tidx[k];
+        const int pb = flat / V, tok = flat - pb * V;                        // :309-310
+        const int64_t pr = r0 + pb;
+        const int64_t h = qi * c.hyps_per_query + c.hyp_base + k;
+        st.hyp_score[h] = S.tval[k];                                         // :662-668
+        st.hyp_len[h] = new_len;
+        st.hyp_valid[h] = S.tvalid[k];
+        int32_t* ht = st.hyp_tokens + h * c.T;
+        const int32_t* pt = st.tokens_in + pr * c.T;
+        for (int i = 0; i < c.cur_len; ++i) ht[i] = pt[i];
+        ht[c.cur_len] = tok;
+        for (int i = new_len; i < c.T; ++i) ht[i] = c.pad_token_id;
+        if (st.hyp_lo) {
+            uint64_t l = 0, r = 0;
+            if (!c.disable_fm_index && S.tvalid[k] && !(c.forced_bos_token_id >= 0 && c.cur_len == 1)) {
+                uint64_t rr;
+                lf_step(fm, (uint64_t)tok + c.shift, st.lo_in[pr], st.hi_in[pr] - 1, l, rr);
+                r = rr + 1;
+            }
+            st.hyp_lo[h] = l; st.hyp_hi[h] = r;
+        }
+    }
+    // ---- next beams: state of row j comes from candidate nbeam_src[j] ------------------------------
+    if (tid < B) {
+        const int j = tid;
+        const int64_t nr = r0 + j;
+        if (j < S.n_noneos) {
+            const int k = S.nbeam_src[j];
+            const int flat = S.tidx[k];
+            const int pb = flat / V, tok = flat - pb * V;
+            const int64_t pr = r0 + pb;
+            st.beam_scores_out[nr] = S.tval[k];
+            const int32_t* pt = st.tokens_in + pr * c.T;
+            int32_t* nt = st.tokens_out + nr * c.T;
+            for (int i = 0; i < c.cur_len; ++i) nt[i] = pt[i];
+            nt[c.cur_len] = tok;
+            for (int i = new_len; i < c.T; ++i) nt[i] = c.pad_token_id;
+            const int32_t* pa = st.anc_in + pr * c.T;
+            int32_t* na = st.anc_out + nr * c.T;
+            for (int i = 0; i + 1 < c.cur_len; ++i) na[i] = pa[i];
+            na[c.cur_len - 1] = (int32_t)pr;                                // KV of position cur_len-1 lives in the parent's slot
+            uint64_t l = 0, rr = 0;
+            if (c.forced_bos_token_id >= 0 && c.cur_len == 1) {
+                // the forced BOS is not part of the FM-index query (the reference drops it, :71)
+                l = st.lo_in[pr]; rr = st.hi_in[pr];
+            } else if (!c.disable_fm_index) {
+                // incremental get_range: one backward_search_step on the parent's range
+                // (seal/index.py:102-111 recomputed from scratch by the reference, :96-101)
+                lf_step(fm, (uint64_t)tok + c.shift, st.lo_in[pr], st.hi_in[pr] - 1, l, rr);
+                rr += 1;
+            }
+            st.lo_out[nr] = l; st.hi_out[nr] = rr;
+            st.pw_out[nr] = (c.forced_bos_token_id >= 0 && c.cur_len == 1) ? st.pw_in[pr] : st.hi_in[pr] - st.lo_in[pr];
+        } else {
+            st.beam_scores_out[nr] = 0.f;
+            st.lo_out[nr] = 0; st.hi_out[nr] = 0; st.pw_out[nr] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- successor sets of the new beams -> next step's masks (distinct_count_multi, :107) ---------
+    if (c.expand_next && !c.disable_fm_index) {
+        const int warp = tid >> 5, lane = tid & 31, nw = kSelThreads / 32;
+        for (int j = warp; j < B; j += nw) {
+            const int64_t nr = r0 + j;
+            uint32_t* row = st.mask_out + nr * c.mask_words;
+            for (int w = lane; w < c.mask_words; w += 32) row[w] = 0;
+            __syncwarp();
+            MaskSink sink{row, (uint32_t)V, (uint32_t)c.shift};
+            warp_expand(fm, st.lo_out[nr], st.hi_out[nr], sink, S.frontier[warp]);
+            __syncwarp();
+        }
+    }
+}
+
+// BeamSearchScorerWithMemory.finalize (seal/beam_search.py:705-725): the live beams are recorded
+// once more with their running scores.
+__global__ void finalize_kernel(int64_t Q, StepCfg c, const float* __restrict__ beam_scores,
+                                const int32_t* __restrict__ tokens, const uint64_t* __restrict__ lo,
+                                const uint64_t* __restrict__ hi, StepState st) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= Q * c.num_beams) return;
+    const int64_t qi = i / c.num_beams; const int j = (int)(i - qi * c.num_beams);
+    const int64_t h = qi * c.hyps_per_query + c.hyp_base + j;
+    st.hyp_score[h] = beam_scores[i];
+    st.hyp_len[h] = c.cur_len;
+    st.hyp_valid[h] = 2;
+    for (int t = 0; t < c.T; ++t) st.hyp_tokens[h * c.T + t] = tokens[i * c.T + t];
+    if (st.hyp_lo) { st.hyp_lo[h] = lo[i]; st.hyp_hi[h] = hi[i]; }
+}
+
+// ---- stateless logits-processor path (seal/beam_search.py:62-140) -------------------------------
+
+// rows -> (lo, hi, rule) from scratch, like the reference: fold of force_decoding_from + sent[1:]
+__global__ void __launch_bounds__(128) rows_fold_kernel(FmView fm, int64_t R, int t, const int64_t* __restrict__ ids,
+                                                        int skip_first, int eos, int pad, int stop_at_count,
+                                                        const uint64_t* __restrict__ force_syms, int n_force,
+                                                        int shift, uint64_t* __restrict__ lo_out,
+                                                        uint64_t* __restrict__ hi_out, uint8_t* __restrict__ rule_out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t* sent = ids + r * t + skip_first;
+    const int n = t - skip_first;
+    const int64_t last = sent[n - 1];
+    uint64_t l = 0, h = 0, count = 0;
+    const bool ended = (last == eos || last == pad);
+    if (!ended) {
+        uint64_t rr = fm.m, prev_l = 0, prev_r = fm.m;        // get_range starts from (0, size()) (:106-107)
+        for (int i = 0; i < n_force; ++i) { prev_l = l; prev_r = rr; lf_step(fm, force_syms[i], l, rr, l, rr); }
+        for (int i = 1; i < n; ++i) { prev_l = l; prev_r = rr; lf_step(fm, (uint64_t)sent[i] + shift, l, rr, l, rr); }
+        h = rr + 1;
+        count = prev_r + 1 - prev_l;                          // get_count(prefix without the last token) (:97,:101)
+    }
+    uint8_t rule = 0;
+    if (stop_at_count > 0 && count <= (uint64_t)stop_at_count) rule = 1;
+    else if (ended) rule = 2;
+    lo_out[r] = l; hi_out[r] = h; rule_out[r] = rule;
+}
+
+// scores_out = scores_in + mask, mask in {0,-inf}
+__global__ void __launch_bounds__(256) apply_mask_kernel(int64_t R, int V, int64_t ld, const float* __restrict__ in,
+                                                         float* __restrict__ out, const uint32_t* __restrict__ masks,
+                                                         int mask_words, int shared_mask,
+                                                         const uint8_t* __restrict__ rule, int eos, int pad,
+                                                         int always_allow_eos, int only_token) {
+    const int64_t r = blockIdx.y;
+    const uint32_t* mrow = shared_mask ? masks : masks + r * mask_words;
+    const int ru = rule ? rule[r] : 0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        bool allowed;
+        if (only_token >= 0) allowed = v == only_token;
+        else {
+            allowed = ru == 1 ? v == eos : ru == 2 ? v == pad : ((mrow[v >> 5] >> (v & 31)) & 1);
+            if (always_allow_eos && v == eos) allowed = true;
+        }
+        const float x = in[r * ld + v];
+        out[r * ld + v] = allowed ? x + 0.0f : x + (-INFINITY);
+    }
+}
+
+}  // namespace sealb200

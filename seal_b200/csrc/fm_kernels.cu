@@ -3,6 +3,8 @@
 #include "fm_device.cuh"
 #include "fm_host.hpp"
 #include "fm_layout.hpp"
+#include "fm_expand.cuh"
+#include "fm_handle.hpp"
 #include "common.cuh"
 
 #include <cuda_runtime.h>
@@ -65,78 +67,6 @@ __global__ void __launch_bounds__(128) lf_fold_kernel(FmView v, uint64_t nq, con
         out_lo[q] = l;
         out_hi[q] = r + 1;
     }
-}
-
-struct MaskSink {
-    uint32_t* row;        // bitmask row
-    uint32_t vocab, shift;
-    __device__ void operator()(uint32_t symbol, uint64_t, uint64_t) const {
-        // seal/index.py:141,153: the sentinel (0) is dropped, tokens are symbol - SHIFT
-        if (symbol < shift || symbol == 0) return;
-        const uint32_t tok = symbol - shift;
-        if (tok < vocab) atomicOr(row + (tok >> 5), 1u << (tok & 31));
-    }
-};
-struct DenseSink {
-    uint64_t* counts;     // 2^L entries for this range, zeroed
-    __device__ void operator()(uint32_t symbol, uint64_t ri, uint64_t rj) const { counts[symbol] = rj - ri; }
-};
-
-// One warp expands one SA range.  Phase 1: level-synchronous frontier expansion, one lane per
-// frontier node, children compacted in order with a shuffle scan (frontier lives in shared memory).
-// Phase 2: once the frontier is wider than a warp, every lane walks its own subtrees depth-first.
-struct WarpFrontier {
-    uint64_t i[2][64];
-    uint64_t j[2][64];
-    uint32_t prefix[2][64];
-};
-
-template <typename Sink>
-__device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, WarpFrontier& F) {
-    if (lo >= hi) return;                                  // fm_index.cpp:98 `if (low == high) return`
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t L = v.L;
-    uint32_t n = 1, level = 0, cur = 0;
-    if (lane == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; }
-    __syncwarp();
-    while (level < L && n <= 32) {
-        uint32_t nc = 0;
-        uint64_t a = 0, b = 0, ei = 0, ej = 0;
-        uint32_t ep = 0;
-        bool has0 = false, has1 = false;
-        if (lane < n) {
-            ei = F.i[cur][lane]; ej = F.j[cur][lane]; ep = F.prefix[cur][lane];
-            const uint64_t start = v.csym[static_cast<uint64_t>(ep) << (L - level)];
-            const uint64_t o1 = v.node_ones[(1u << level) + ep];
-            const uint64_t base = static_cast<uint64_t>(level) * v.m + start;
-            if (ej == ei + 1) {
-                int bit;
-                a = rank1(v, base + ei, &bit) - o1;
-                b = a + static_cast<uint64_t>(bit);
-            } else {
-                a = rank1(v, base + ei) - o1;
-                b = rank1(v, base + ej) - o1;
-            }
-            has1 = (b - a) != 0;
-            has0 = ((ej - ei) - (b - a)) != 0;
-            nc = (has0 ? 1u : 0u) + (has1 ? 1u : 0u);
-        }
-        uint32_t incl = nc;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (uint32_t)d) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t w = incl - nc;
-        const uint32_t nxt = cur ^ 1;
-        if (has0) { F.i[nxt][w] = ei - a; F.j[nxt][w] = ej - b; F.prefix[nxt][w] = ep << 1; ++w; }
-        if (has1) { F.i[nxt][w] = a; F.j[nxt][w] = b; F.prefix[nxt][w] = (ep << 1) | 1u; }
-        __syncwarp();
-        cur = nxt; n = total; ++level;
-    }
-    for (uint32_t e = lane; e < n; e += 32)
-        expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
 }
 
 constexpr int kExpandWarps = 4;
@@ -301,6 +231,14 @@ void release_device(sealfm_t* h) {
 }
 
 }  // namespace
+
+namespace sealb200 {
+FmView sealfm_view(const sealfm_t* h) {
+    if (!h) throw ApiError(SEALFM_EINVAL, "null handle");
+    if (h->device < 0) throw ApiError(SEALFM_ENODEVICE, "index not bound to a CUDA device (call sealfm_to_device)");
+    return h->view;
+}
+}  // namespace sealb200
 
 // ------------------------------------------------------------------------------------------------
 // C ABI

@@ -1,0 +1,229 @@
+"""GPU parity of the decode path (include/sealdec.h) against the CPU/torch restatement of
+seal/beam_search.py (oracle/decode_oracle.py) driving transformers' BART in eager fp32.
+Integer outputs (tokens, SA ranges, masks) bit-exact; beam scores within 1e-4 (BASELINE.json)."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module", autouse=True)
+def need_gpu():
+    import torch
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+
+
+def tiny_setup(vocab=2000, n_docs=300, doc_len=30, layers=2, d_model=128, seed=3):
+    from oracle.decode_oracle import make_bart
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import make_corpus
+    docs = make_corpus(n_docs=n_docs, doc_len=doc_len, n_phrases=2 * n_docs, seed=seed, vocab=vocab)
+    seqs = [d.tolist() for d in docs]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs, in_memory=True)
+    model = make_bart(seed=0, layers=layers, vocab=vocab, d_model=d_model)
+    return docs, ora, idx, model
+
+
+def make_inputs(rng, Q, S, vocab):
+    import torch
+    ids = torch.tensor(rng.integers(4, vocab, size=(Q, S)), dtype=torch.long)
+    am = torch.ones_like(ids)
+    ids[:, 0] = 0
+    for q in range(Q):
+        l = int(rng.integers(max(3, S // 2), S + 1))
+        ids[q, l - 1] = 2
+        ids[q, l:] = 1
+        am[q, l:] = 0
+    return ids, am
+
+
+def compare_generate(ours, oracle_out, ora, tol=TOL):
+    """ours: [[(score, tokens)]], oracle_out: [[(score, tokens, constrained)]].  Compares, per query,
+    the hypotheses that survive the caller's filter (tokens found in the index)."""
+    assert len(ours) == len(oracle_out)
+    worst = 0.0
+    for q, (a, b) in enumerate(zip(ours, oracle_out)):
+        fa = sorted([(tuple(t), s) for s, t in a if ora.get_count(list(t[1:])) > 0])
+        fb = sorted([(tuple(t), s) for s, t, _ in b if ora.get_count(list(t[1:])) > 0])
+        assert [x[0] for x in fa] == [x[0] for x in fb], (
+            f"query {q}: hypothesis token sets differ\nours-only: {sorted(set(x[0] for x in fa) - set(x[0] for x in fb))[:5]}"
+            f"\noracle-only: {sorted(set(x[0] for x in fb) - set(x[0] for x in fa))[:5]}")
+        for (ta, sa), (tb, sb) in zip(fa, fb):
+            worst = max(worst, abs(sa - sb))
+            assert abs(sa - sb) <= tol, (q, ta, sa, sb)
+    return worst
+
+
+def test_bart_step_logits_vs_hf_tiny():
+    import torch
+    from oracle.decode_oracle import HFBartStepper
+    from seal_b200.beam_search import SealBartEngine
+    docs, ora, idx, model = tiny_setup()
+    eng = SealBartEngine.from_hf(model, device=0)
+    rng = np.random.default_rng(1)
+    ids, am = make_inputs(rng, Q=3, S=11, vocab=2000)
+    B = 4
+    for t in (1, 2, 5):
+        dec = torch.tensor(rng.integers(4, 2000, size=(3 * B, t)), dtype=torch.long); dec[:, 0] = 2
+        ref = HFBartStepper(model, ids, am, B)(dec).numpy()
+        got = eng.debug_step_logits(ids.numpy(), am.numpy(), B, dec.numpy())
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin)
+        err = np.abs(got[fin] - ref[fin]).max()
+        print(f"tiny t={t}: max |dlogit| = {err:.3e}")
+        assert err < 2e-5, (t, err)
+
+
+def test_bart_step_logits_vs_hf_bart_large():
+    """BartConfig() == bart-large, seeded random weights; teacher-forced logits at t=1 and t=4."""
+    import torch
+    from oracle.decode_oracle import make_bart, HFBartStepper
+    from seal_b200.beam_search import SealBartEngine
+    model = make_bart(seed=0)
+    eng = SealBartEngine.from_hf(model, device=0)
+    rng = np.random.default_rng(2)
+    ids, am = make_inputs(rng, Q=2, S=9, vocab=50265)
+    B = 3
+    for t in (1, 4):
+        dec = torch.tensor(rng.integers(4, 50265, size=(2 * B, t)), dtype=torch.long); dec[:, 0] = 2
+        ref = HFBartStepper(model, ids, am, B)(dec).numpy()
+        got = eng.debug_step_logits(ids.numpy(), am.numpy(), B, dec.numpy())
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin)
+        err = np.abs(got[fin] - ref[fin]).max()
+        lp_ref = torch.log_softmax(torch.tensor(ref), -1).numpy(); lp_got = torch.log_softmax(torch.tensor(got), -1).numpy()
+        lerr = np.abs(lp_got[fin] - lp_ref[fin]).max()
+        print(f"bart-large t={t}: max |dlogit| = {err:.3e}, max |dlogprob| = {lerr:.3e}")
+        assert lerr < 1e-5, (t, err, lerr)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_beams=5, min_length=8, max_length=8, length_penalty=0.0),
+    dict(num_beams=3, min_length=2, max_length=6, length_penalty=1.0),
+    dict(num_beams=4, min_length=0, max_length=7, length_penalty=0.0, always_allow_eos=True),
+    dict(num_beams=4, min_length=0, max_length=7, length_penalty=0.0, stop_at_count=3),
+    dict(num_beams=5, min_length=3, max_length=7, length_penalty=0.0, force_decoding_from="doc"),
+    dict(num_beams=3, min_length=0, max_length=6, length_penalty=0.0, forced_bos_token_id=0),
+    dict(num_beams=4, min_length=0, max_length=6, length_penalty=0.0, disable_fm_index=True),
+    dict(num_beams=15, min_length=10, max_length=10, length_penalty=0.0),
+])
+def test_fm_index_generate_vs_oracle_tiny(kw):
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200.beam_search import fm_index_generate
+    docs, ora, idx, model = tiny_setup()
+    kw = dict(kw)
+    if kw.get("force_decoding_from") == "doc":
+        kw["force_decoding_from"] = docs[5].tolist()[3:5]
+    rng = np.random.default_rng(4)
+    ids, am = make_inputs(rng, Q=6, S=12, vocab=2000)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    worst = compare_generate(got, exp, ora)
+    print(f"{kw}: worst |dscore| = {worst:.3e}; hyps/query = {[len(x) for x in got]}")
+    if not kw.get("disable_fm_index"):
+        assert max(len(x) for x in got) > kw["num_beams"]
+
+
+def test_fm_index_generate_sample_corpus_bart_large():
+    """BASELINE.json configs[0]: the README's 3-document sample (README.md:149-153) through a fixed
+    toy word->id table, 1 query, beam 5, bart-large (seeded random weights)."""
+    import torch
+    from oracle.decode_oracle import make_bart, fm_index_generate_oracle
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.beam_search import fm_index_generate, generate_records
+    from seal_b200.index import FMIndex
+    corpus = ["Doc 1 @@ This is a sample document",
+              "Doc 2 @@ And here you find the final one",
+              "Doc 3 @@ This is another sample document"]
+    words = sorted({w for line in corpus for w in line.split()})
+    table = {w: 1000 + 7 * i for i, w in enumerate(words)}
+    seqs = [[table[w] for w in line.split()] + [2] for line in corpus]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs, in_memory=True)
+    assert idx.occurring_distinct == ora.occurring_distinct
+    model = make_bart(seed=0)
+    ids = torch.tensor([[0, 1000, 1007, 1014, 1021, 2]]); am = torch.ones_like(ids)
+    kw = dict(num_beams=5, min_length=10, max_length=10, length_penalty=0.0)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    worst = compare_generate(got, exp, ora)
+    print(f"sample corpus: worst |dscore| = {worst:.3e}, {len(got[0])} hyps")
+    # SA ranges reported for valid hypotheses equal the oracle's get_range
+    rec = generate_records(model, idx, ids, am, **kw)
+    n = 0
+    for h in range(rec["scores"].shape[1]):
+        if rec["valid"][0, h] == 1:
+            toks = rec["tokens"][0, h, : rec["lens"][0, h]].tolist()
+            assert (int(rec["lo"][0, h]), int(rec["hi"][0, h])) == ora.get_range(toks[1:]), toks
+            n += 1
+    assert n > 0
+
+
+def test_fm_index_generate_bart_large_batch20_beam15():
+    """The reference's operating point (README.md:76-83): batch 20, beam 15, body n-grams of 10,
+    on a 200 k-token phrase corpus; oracle = HF BART eager fp32 on the same GPU + CPU FM oracle."""
+    import torch
+    from oracle.decode_oracle import make_bart, fm_index_generate_oracle
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.beam_search import fm_index_generate
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import make_corpus, make_queries
+    docs = make_corpus(n_docs=2000, doc_len=100, n_phrases=4000, seed=21)
+    seqs = [d.tolist() for d in docs]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs, in_memory=True)
+    model = make_bart(seed=0)
+    ids, am = make_queries(20, seed=77)
+    ids = torch.tensor(ids); am = torch.tensor(am)
+    kw = dict(num_beams=15, min_length=10, max_length=10, length_penalty=0.0)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    model_gpu = model.to("cuda")
+    exp = fm_index_generate_oracle(model_gpu, ora, ids.cuda(), am.cuda(), **kw)
+    worst = compare_generate(got, exp, ora)
+    print(f"batch20/beam15: worst |dscore| = {worst:.3e}; hyps/query min {min(len(x) for x in got)} max {max(len(x) for x in got)}")
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),
+    dict(always_allow_eos=True),
+    dict(stop_at_count=2),
+    dict(force_decoding_from="doc"),
+    dict(forced_bos_token_id=0),
+])
+def test_index_based_logits_processor_vs_oracle(kw):
+    """Stateless HF-protocol hook, seal/beam_search.py:62-140: exact mask equality (scores + {0,-inf})."""
+    import torch
+    from oracle.decode_oracle import IndexBasedLogitsProcessorOracle
+    from seal_b200.beam_search import IndexBasedLogitsProcessor
+    docs, ora, idx, _ = tiny_setup(layers=1)
+    kw = dict(kw)
+    if kw.get("force_decoding_from") == "doc":
+        kw["force_decoding_from"] = docs[9].tolist()[2:4]
+    V, B, nb = 2000, 4, 3
+    rng = np.random.default_rng(8)
+    po = IndexBasedLogitsProcessorOracle(ora, B, pad_token_id=1, eos_token_id=2, **kw)
+    pg = IndexBasedLogitsProcessor(idx, B, pad_token_id=1, eos_token_id=2, **kw)
+    for t in (1, 2, 3, 5):
+        rows = []
+        for r in range(nb * B):
+            d = docs[int(rng.integers(0, len(docs)))].tolist()
+            a = int(rng.integers(0, len(d) - 8))
+            sent = [2] + d[a:a + t - 1]
+            u = rng.random()
+            if t > 1 and u < 0.15: sent[-1] = 2              # row that ended in eos
+            elif t > 1 and u < 0.25: sent[-1] = 1            # ... in pad
+            elif t > 1 and u < 0.35: sent[-1] = int(rng.integers(4, V))   # token that breaks the n-gram
+            rows.append(sent)
+        ids = torch.tensor(rows, dtype=torch.long)
+        scores = torch.randn(nb * B, V)
+        exp = po(ids.clone(), scores.clone())
+        got = pg(ids.cuda(), scores.cuda()).cpu()
+        assert torch.equal(torch.isinf(exp), torch.isinf(got)), (t, kw)
+        fin = ~torch.isinf(exp)
+        assert torch.equal(exp[fin], got[fin])
