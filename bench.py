@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Headline benchmark: SEAL constrained beam-search decode, queries/sec at beam 15 on a synthetic
+10 M-token FM-index with BART-large (BASELINE.json metric / configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on host cores
+
+One "step" = one full pass of the hot path (encoder, 9 constrained decode steps, hypothesis
+records) over one batch of `--queries` synthetic queries.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec at beam=15, 1k queries, 10M-token index; rank-kernel HBM GB/s"
+BEAM, MIN_LEN, MAX_LEN, LP = 15, 10, 10, 0.0          # SEALSearcher body defaults (retrieval.py:70-83)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(n_queries, seed):
+    from seal_b200.synthetic import make_corpus, make_queries
+    docs = make_corpus()                                     # 100 000 docs x 100 tokens, seed 1234
+    ids, mask = make_queries(n_queries, seed=seed)
+    return docs, ids, mask
+
+
+def make_model():
+    import torch
+    from transformers import BartConfig, BartForConditionalGeneration
+    cfg = BartConfig()                                       # defaults == facebook/bart-large
+    cfg.forced_bos_token_id = None                           # seal/retrieval.py:566,580
+    torch.manual_seed(0)
+    model = BartForConditionalGeneration(cfg).eval().float()
+    with torch.no_grad():
+        for t in (cfg.pad_token_id, cfg.bos_token_id, cfg.vocab_size - 1):
+            model.final_logits_bias[0, t] = float("-inf")    # seal/retrieval.py:584-588
+    return model
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    from seal_b200._lib import lib, check
+    from seal_b200.beam_search import SealBartEngine, _make_params, _occurring_mask, generate_records
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import corpus_symbols
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    Q = args.queries
+    docs, ids_np, mask_np = build_inputs(Q, seed=4321 + rank)          # every rank: its own 1k queries
+    # build straight from the symbol stream (same result as FMIndex.initialize, without 100k Python lists)
+    from seal_b200.cpp_modules.fm_index import FMIndex as RawFM
+    index = FMIndex()
+    RawFM.initialize(index, corpus_symbols(docs))
+    index.beginnings = list(range(0, docs.size + 1, docs.shape[1]))
+    index._sync_beginnings()
+    index.to_device(local)
+    index.occurring_distinct, index.occurring_counts = index.get_distinct_count(0, len(index))
+    model = make_model()
+    eng = SealBartEngine.from_hf(model, device=local, gemm_mode=args.gemm_mode)
+    cfg = model.config
+    del model
+    p = _make_params(cfg, BEAM, MIN_LEN, MAX_LEN, LP, cfg.eos_token_id, None, False, False, 0, None)
+    H = int(lib.sealdec_hyps_per_query(C.byref(p))); T = MAX_LEN
+    S = ids_np.shape[1]
+    occ_np = _occurring_mask(index, cfg.vocab_size)
+    occ = torch.from_numpy(occ_np.view(np.int32)).to(dev)
+    ids = torch.from_numpy(ids_np).to(dev); mask = torch.from_numpy(mask_np).to(dev)
+    o_score = torch.empty((Q, H), dtype=torch.float32, device=dev); o_len = torch.empty((Q, H), dtype=torch.int32, device=dev)
+    o_tok = torch.empty((Q, H, T), dtype=torch.int32, device=dev); o_valid = torch.empty((Q, H), dtype=torch.uint8, device=dev)
+    o_lo = torch.empty((Q, H), dtype=torch.int64, device=dev); o_hi = torch.empty((Q, H), dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    rec_bytes = Q * H * (4 + 4 + 4 * T + 1 + 16)
+    gathered = [torch.empty_like(o_score) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def step_device():
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.sealdec_generate_d(eng._h, index._dev(), occ.data_ptr(), C.byref(p), ids.data_ptr(), mask.data_ptr(),
+                                     Q, S, st, o_score.data_ptr(), o_len.data_ptr(), o_tok.data_ptr(), o_valid.data_ptr(),
+                                     o_lo.data_ptr(), o_hi.data_ptr(), err.data_ptr()))
+        if world > 1:                                   # the single collective: result records to rank 0
+            dist.gather(o_score, gathered, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.last_launch_count() * args.steps
+    phases = eng.last_phase_us()
+    assert int(err.item()) == 0
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * Q * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call (H2D inputs + D2H records inside) ----------
+    pin_ids = torch.from_numpy(ids_np).pin_memory(); pin_mask = torch.from_numpy(mask_np).pin_memory()
+    for _ in range(min(args.warmup, 2)):
+        generate_records(eng, index, pin_ids.numpy(), pin_mask.numpy(), MIN_LEN, MAX_LEN, LP, BEAM, forced_bos_token_id=None)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        rec = generate_records(eng, index, pin_ids.numpy(), pin_mask.numpy(), MIN_LEN, MAX_LEN, LP, BEAM, forced_bos_token_id=None)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    e2e = {"value": world * Q * e2e_steps / e2e_s, "unit": "queries/s",
+           "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes + occ_np.nbytes),
+           "d2h_bytes_per_step": int(rec_bytes + 4), "api": "sealdec_generate (host buffers)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf_burst, tf_sus, which = peaks()
+    # ---- roofline of the dominant kernel (the decoder/lm_head GEMM) ----------------------------------
+    R = Q * BEAM; d = cfg.d_model; V = cfg.vocab_size; Ld = cfg.decoder_layers
+    flops_layers = 2.0 * R * (12 * d * d + 2 * d * cfg.decoder_ffn_dim) * Ld * (MAX_LEN - 1)   # qkv,o,cq,co + fc1,fc2
+    flops_head = 2.0 * R * d * V * (MAX_LEN - 1)
+    gemm_s = (phases["decoder_layers"] + phases["lm_head"]) * 1e-6
+    n_gemm = (7 * Ld + 1) * (MAX_LEN - 1)
+    roof = {"bound": "tensor", "kernel": "sgemm_tn_kernel" if args.gemm_mode == 0 else "tf32x3_umma_gemm",
+            "achieved": (flops_layers + flops_head) / gemm_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
+            "frac": (flops_layers + flops_head) / gemm_s / 1e12 / tf_sus, "traffic": None,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",
+            "note": "algorithmic decoder+lm_head GEMM flops / CUDA-event time of the decoder-layer and lm_head "
+                    "phases (includes the small attention/LN kernels between GEMMs); avg per GEMM launch "
+                    f"{gemm_s / n_gemm * 1e6:.1f} us over {n_gemm} launches"}
+    # FM-index share: select+expand kernel (rank kernel of the metric), algorithmic bytes unknown per
+    # trace here -> report time share; tools/fm_microbench.py reports GB/s on recorded traces.
+    out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "configs[1]: synthetic 10M-token corpus (100k docs x 100 tok, seed 1234), "
+                                  f"{Q} queries/GPU (seed 4321+rank), beam {BEAM}, min=max_length {MAX_LEN}, BART-large "
+                                  "random init seed 0, fp32", "queries_per_gpu": Q, "beam": BEAM, "decode_steps": MAX_LEN - 1,
+                      "parallelism": f"query-sharded x{world}, index+weights replicated, one NCCL gather",
+                      "l2": "per-step working set (KV cache + logits > 10 GB) exceeds L2; no explicit flush"},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+           "roofline": roof, "phases_us_last_step": phases,
+           "cpu_baseline": cpu_baseline_sample(args)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_setup(n_queries, seed=4321):
+    """The reference algorithm on host cores: CPU restatement of seal/beam_search.py (oracle/
+    decode_oracle.py) on transformers' eager fp32 BART + the reference FM-index (oracle/_ref, the
+    unmodified seal/cpp_modules/fm_index.cpp on sdsl-lite; the C port if _ref was not shipped)."""
+    import torch
+    from oracle.fm_oracle import OracleIndex, RefFM, PortFM, ref_available
+    from seal_b200.synthetic import corpus_symbols
+    docs, ids, mask = build_inputs(n_queries, seed)
+    fm = RefFM(corpus_symbols(docs)) if ref_available() else PortFM(corpus_symbols(docs))
+    idx = OracleIndex(_raw=fm)
+    idx.beginnings = list(range(0, docs.size + 1, docs.shape[1]))
+    idx.occurring_distinct, idx.occurring_counts = idx.get_distinct_count(0, len(idx))
+    model = make_model()
+    return idx, model, torch.from_numpy(ids), torch.from_numpy(mask), ("reference" if ref_available() else "port")
+
+
+def reference_step(idx, model, ids, mask, lo, n):
+    from oracle.decode_oracle import fm_index_generate_oracle
+    return fm_index_generate_oracle(model, idx, ids[lo:lo + n], mask[lo:lo + n], min_length=MIN_LEN, max_length=MAX_LEN,
+                                    length_penalty=LP, num_beams=BEAM)
+
+
+def cpu_baseline_sample(args):
+    if args.no_cpu_baseline:
+        return None
+    try:
+        import torch
+        n = args.ref_queries
+        idx, model, ids, mask, kind = reference_setup(max(n, 1))
+        t0 = time.perf_counter()
+        reference_step(idx, model, ids, mask, 0, n)
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": kind,
+                "sample": f"{n} of the 1000 queries, full 9-step constrained decode (HF BART eager fp32 on CPU + "
+                          f"{'sdsl-lite FM-index (oracle/_ref)' if kind == 'reference' else 'C port of the FM-index'}), {dt:.1f} s"}
+    except Exception as ex:  # pragma: no cover
+        return {"value": None, "unit": "queries/s", "error": repr(ex)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    n = args.ref_queries
+    idx, model, ids, mask, kind = reference_setup(n * (args.steps + args.warmup))
+    k = 0
+    for _ in range(args.warmup):
+        reference_step(idx, model, ids, mask, k, n); k += n
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        reference_step(idx, model, ids, mask, k, n); k += n
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    base = {"value": v, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{n} queries per step (bounded sample of the 1000-query batch), 9 decode steps, beam {BEAM}"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "queries/s",
+                      "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "configs[1] sample: synthetic 10M-token corpus, beam 15, min=max_length 10, "
+                                             "BART-large random init seed 0, fp32, host cores only", "queries_per_step": n},
+                      "cpu_baseline": base,
+                      "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--queries", type=int, default=1000)
+    ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference sample")
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("SEALB200_GEMM", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

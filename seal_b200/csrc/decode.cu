@@ -418,11 +418,7 @@ int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d,
         c.stop_at_count = p->stop_at_count; c.always_allow_eos = p->always_allow_eos; c.disable_fm_index = p->disable_fm_index;
         c.remove_invalid_values = p->remove_invalid_values; c.shift = p->shift; c.T = T; c.mask_words = D.W;
         c.hyps_per_query = sealdec_hyps_per_query(p);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
-            attr_set = true;
-        }
+        CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
         std::vector<cudaEvent_t> ev_a, ev_b, ev_c, ev_d;
         int cur = 0;
         for (int step = 0; step + 1 < T; ++step) {
@@ -558,7 +554,7 @@ int sealdec_apply_index_mask_d(const sealfm_t* fm, sealfm_stream_t stream, const
         cudaStream_t s = (cudaStream_t)stream;
         const FmView view = sealfm_view(fm);
         const int W = (int)((V + 31) / 32);
-        dim3 grid(std::min<int64_t>((V + 255) / 256, 64), (unsigned)R);
+        dim3 grid((unsigned)R, (unsigned)std::min<int64_t>((V + 255) / 256, 64));
         const bool fb = cfg->forced_bos_token_id >= 0;
         if (fb && t == 1) {                                                     // :66-69
             apply_mask_kernel<<<grid, 256, 0, s>>>(R, (int)V, ld, in_d, out_d, nullptr, W, 1, nullptr, cfg->eos_token_id,

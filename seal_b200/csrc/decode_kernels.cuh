@@ -404,10 +404,10 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(int64_t R, int V, int64
                                                          int mask_words, int shared_mask,
                                                          const uint8_t* __restrict__ rule, int eos, int pad,
                                                          int always_allow_eos, int only_token) {
-    const int64_t r = blockIdx.y;
+    const int64_t r = blockIdx.x;
     const uint32_t* mrow = shared_mask ? masks : masks + r * mask_words;
     const int ru = rule ? rule[r] : 0;
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < V; v += gridDim.y * blockDim.x) {
         bool allowed;
         if (only_token >= 0) allowed = v == only_token;
         else {
