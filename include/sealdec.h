@@ -129,6 +129,11 @@ int sealdec_generate_d(sealbart_t* model, const sealfm_t* fm, const uint32_t* oc
 int sealdec_debug_step_logits(sealbart_t* model, const int64_t* input_ids, const int64_t* attention_mask,
                               int64_t Q, int64_t S, int32_t num_beams, const int64_t* decoder_input_ids,
                               int64_t t, float* out_logits);
+/* Stand-alone GEMM C[M,N] = A[M,K] W[N,K]^T + bias (+GELU) through the model's GEMM kernels
+ * (mode 0 = fp32 SIMT, 1 = 3xTF32 tcgen05), host pointers; if iters > 0 also reports the average
+ * device time per call (CUDA events, includes the activation split in mode 1). */
+int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A, const float* W,
+                       const float* bias, float* C, int32_t gelu, int32_t iters, double* avg_us);
 /* kernel launches issued by the last sealdec_generate* call on this model (own kernels only) */
 int64_t sealdec_last_launch_count(const sealbart_t* model);
 /* microseconds spent (CUDA events) in the last generate, split by phase:

@@ -99,6 +99,8 @@ _DEC_SIGS = {
     "sealdec_generate_d": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp,
                                  vp, vp, vp]),
     "sealdec_debug_step_logits": (i32, [vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, vp]),
+    "sealdec_debug_gemm": (i32, [i32, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32,
+                                 C.POINTER(C.c_double)]),
     "sealdec_last_launch_count": (C.c_int64, [vp]),
     "sealdec_last_phase_us": (i32, [vp, C.POINTER(C.c_double)]),
 }

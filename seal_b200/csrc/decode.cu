@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "decode_kernels.cuh"
 #include "fm_handle.hpp"
+#include "umma_gemm.cuh"
 
 #include <cuda_runtime.h>
 
@@ -20,7 +21,11 @@ using namespace sealb200;
 
 namespace {
 
-struct Lin { float* w = nullptr; float* b = nullptr; int out = 0, in = 0; };
+struct Lin {
+    float* w = nullptr; float* b = nullptr; int out = 0, in = 0;
+    float* w_hi = nullptr; float* w_lo = nullptr;          // TF32 split copies (gemm_mode 1)
+    CUtensorMap map_hi{}, map_lo{}; bool maps_ready = false;
+};
 struct LNp { float* g = nullptr; float* b = nullptr; };
 struct EncLayerW { Lin qkv, o, fc1, fc2; LNp ln_attn, ln_final; };
 struct DecLayerW { Lin qkv, o, cq, ckv, co, fc1, fc2; LNp ln_self, ln_cross, ln_final; };
@@ -46,6 +51,7 @@ struct sealbart {
     float* lm_head = nullptr; float* final_bias = nullptr;
     bool lm_head_given = false;
     LNp enc_ln_emb, dec_ln_emb;
+    Lin head;
     std::vector<EncLayerW> enc;
     std::vector<DecLayerW> dec;
     struct Slot { float* dst; uint64_t numel; };
@@ -58,7 +64,8 @@ struct sealbart {
     Buf enc_tok, enc_mask, ex, eqkv, eattn, etmp, effn, ckv;
     Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
     Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
-    Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms;
+    Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo;
+    std::vector<void*> split_allocs;
     int64_t launches = 0;
     double phase_us[5] = {0, 0, 0, 0, 0};
     std::vector<cudaEvent_t> events;
@@ -133,15 +140,75 @@ void build_slots(sealbart* m) {
 // ---- launch helpers ----------------------------------------------------------------------------
 struct Ctx { sealbart* m; cudaStream_t s; };
 
-void gemm(Ctx& cx, int64_t M, int N, int K, const float* A, int lda, const Lin& l, float* C, int ldc, bool gelu,
-          const float* bias_override = nullptr, const float* w_override = nullptr) {
+// ---- TMA descriptors ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) throw ApiError(SEALFM_ECUDA, "cuTensorMapEncodeTiled unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// row-major [rows][K] fp32, box = 32 (K) x box_rows, 128B swizzle, zero fill out of bounds
+void make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
+    cuuint64_t dims[2] = {K, rows};
+    cuuint64_t strides[1] = {ld * sizeof(float)};
+    cuuint32_t box[2] = {UK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw ApiError(SEALFM_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
+constexpr int kUmmaBN = 256;
+
+void split_into(cudaStream_t s, const float* x, float* hi, float* lo, uint64_t numel) {
+    const int64_t n4 = (int64_t)(numel / 4);
+    const int blocks = (int)std::min<int64_t>((n4 + 255) / 256, (int64_t)sm_count() * 8);
+    split_tf32_kernel<<<std::max(blocks, 1), 256, 0, s>>>(n4, reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                          reinterpret_cast<float4*>(lo));
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& whi,
+                 const CUtensorMap& wlo, const float* bias, float* C, int ldc, bool gelu) {
+    using SMm = UmmaSmem<kUmmaBN>;
+    dim3 grid((N + kUmmaBN - 1) / kUmmaBN, (unsigned)((M + UM - 1) / UM));
+    if (gelu) {
+        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+        umma_gemm_tf32x3_kernel<kUmmaBN, true><<<grid, UTHREADS, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C, ldc);
+    } else {
+        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+        umma_gemm_tf32x3_kernel<kUmmaBN, false><<<grid, UTHREADS, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C, ldc);
+    }
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void gemm(Ctx& cx, int64_t M, int N, int K, const float* A, int lda, Lin& l, float* C, int ldc, bool gelu) {
     if (M == 0) return;
+    sealbart* m = cx.m;
+    if (m->cfg.gemm_mode == 1 && K % UK == 0 && lda == K && l.w_hi) {
+        // 3xTF32 on tcgen05: split the activations, weights were split once at finalize
+        float* ahi = m->a_hi.as<float>(); float* alo = m->a_lo.as<float>();
+        split_into(cx.s, A, ahi, alo, (uint64_t)M * K); m->launches++;
+        CUtensorMap mah, mal;
+        make_map(&mah, ahi, M, K, K, UM); make_map(&mal, alo, M, K, K, UM);
+        if (!l.maps_ready) { make_map(&l.map_hi, l.w_hi, N, K, K, kUmmaBN); make_map(&l.map_lo, l.w_lo, N, K, K, kUmmaBN); l.maps_ready = true; }
+        umma_launch(cx.s, M, N, K, mah, mal, l.map_hi, l.map_lo, l.b, C, ldc, gelu);
+        m->launches++;
+        return;
+    }
     if (K % GBK) throw ApiError(SEALFM_EINVAL, "GEMM K must be a multiple of 16");
-    const float* W = w_override ? w_override : l.w;
-    const float* bias = bias_override ? bias_override : l.b;
     dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
-    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, W, K, bias, C, ldc);
-    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, W, K, bias, C, ldc);
+    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, l.w, K, l.b, C, ldc);
+    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, l.w, K, l.b, C, ldc);
     CUDA_CHECK(cudaGetLastError());
     cx.m->launches++;
 }
@@ -194,6 +261,10 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_scores.ensure(2 * D.R * 4); m->st_tokens.ensure(2 * D.R * D.T * 4);
     m->st_lo.ensure(2 * D.R * 8); m->st_hi.ensure(2 * D.R * 8); m->st_pw.ensure(2 * D.R * 8);
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
+    if (m->cfg.gemm_mode == 1) {
+        const size_t mx = (size_t)std::max<int64_t>(Tk, D.R) * std::max(D.f, D.d) * 4;
+        m->a_hi.ensure(mx); m->a_lo.ensure(mx);
+    }
     m->err.ensure(4);
 }
 
@@ -262,8 +333,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     }
     if (ev_layers_done) CUDA_CHECK(cudaEventRecord(ev_layers_done, cx.s));
     if (want_logits) {
-        Lin head; head.w = m->lm_head; head.b = m->final_bias; head.out = D.V; head.in = d;
-        gemm(cx, R, D.V, d, x, d, head, m->logits.as<float>(), D.ld, false);
+        gemm(cx, R, D.V, d, x, d, m->head, m->logits.as<float>(), D.ld, false);
     }
 }
 
@@ -311,11 +381,12 @@ void sealbart_free(sealbart_t* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     for (void* p : m->allocs) cudaFree(p);
+    for (void* p : m->split_allocs) cudaFree(p);
     if (m->lm_head_given) cudaFree(m->lm_head);
     for (Buf* b : {&m->enc_tok, &m->enc_mask, &m->ex, &m->eqkv, &m->eattn, &m->etmp, &m->effn, &m->ckv, &m->dx, &m->dqkv,
                    &m->dattn, &m->dtmp, &m->dcq, &m->dffn, &m->logits, &m->kc, &m->vc, &m->st_scores, &m->st_tokens,
                    &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->hy_score, &m->hy_len, &m->hy_tok,
-                   &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms})
+                   &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms, &m->a_hi, &m->a_lo})
         b->release();
     for (auto e : m->events) cudaEventDestroy(e);
     delete m;
@@ -349,6 +420,24 @@ int sealbart_finalize(sealbart_t* m) {
         for (auto& kv : m->slots)
             if (!m->loaded.count(kv.first)) throw ApiError(SEALFM_EINVAL, "state_dict tensor missing: " + kv.first);
         if (!m->lm_head_given) m->lm_head = m->shared;          // tied (seal/utils.py:48-49)
+        m->head.w = m->lm_head; m->head.b = m->final_bias; m->head.out = m->cfg.vocab_size; m->head.in = m->cfg.d_model;
+        if (m->cfg.gemm_mode == 1) {
+            CUDA_CHECK(cudaSetDevice(m->device));
+            for (void* p : m->split_allocs) cudaFree(p);
+            m->split_allocs.clear();
+            auto split_lin = [&](Lin& l) {
+                const uint64_t n = (uint64_t)l.out * l.in;
+                CUDA_CHECK(cudaMalloc(&l.w_hi, n * 4)); m->split_allocs.push_back(l.w_hi);
+                CUDA_CHECK(cudaMalloc(&l.w_lo, n * 4)); m->split_allocs.push_back(l.w_lo);
+                split_into(nullptr, l.w, l.w_hi, l.w_lo, n);
+                l.maps_ready = false;
+                m->weight_bytes += 2 * n * 4;
+            };
+            for (auto& L : m->enc) { split_lin(L.qkv); split_lin(L.o); split_lin(L.fc1); split_lin(L.fc2); }
+            for (auto& L : m->dec) { split_lin(L.qkv); split_lin(L.o); split_lin(L.cq); split_lin(L.ckv); split_lin(L.co); split_lin(L.fc1); split_lin(L.fc2); }
+            split_lin(m->head);
+            CUDA_CHECK(cudaDeviceSynchronize());
+        }
         m->finalized = true;
     });
 }
@@ -539,6 +628,45 @@ int sealdec_debug_step_logits(sealbart_t* m, const int64_t* ids, const int64_t* 
         CUDA_CHECK(cudaMemcpy2DAsync(out_logits, (size_t)D.V * 4, m->logits.p, (size_t)D.ld * 4, (size_t)D.V * 4, D.R,
                                      cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A, const float* W, const float* bias, float* C,
+                       int32_t gelu, int32_t iters, double* avg_us) {
+    return guarded([&] {
+        if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) throw ApiError(SEALFM_EINVAL, "bad argument");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); throw ApiError(SEALFM_ENODEVICE, "no CUDA device available"); }
+        sealbart fake; fake.cfg.gemm_mode = mode;
+        CUDA_CHECK(cudaGetDevice(&fake.device));
+        Buf dA, dW, dB, dC, whi, wlo;
+        struct Rel { std::vector<Buf*> v; sealbart* f; ~Rel() { for (auto b : v) b->release(); f->a_hi.release(); f->a_lo.release(); } } rel{{&dA, &dW, &dB, &dC, &whi, &wlo}, &fake};
+        const int ldc = (N + 3) / 4 * 4;
+        dA.ensure((size_t)M * K * 4); dW.ensure((size_t)N * K * 4); dB.ensure((size_t)N * 4); dC.ensure((size_t)M * ldc * 4);
+        CUDA_CHECK(cudaMemcpy(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(dW.p, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
+        if (bias) CUDA_CHECK(cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+        Lin l; l.w = dW.as<float>(); l.b = bias ? dB.as<float>() : nullptr; l.out = N; l.in = K;
+        if (mode == 1) {
+            whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
+            l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
+            split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);
+            fake.a_hi.ensure((size_t)M * K * 4); fake.a_lo.ensure((size_t)M * K * 4);
+        }
+        Ctx cx{&fake, nullptr};
+        gemm(cx, M, N, K, dA.as<float>(), K, l, dC.as<float>(), ldc, gelu != 0);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        if (iters > 0 && avg_us) {
+            cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+            CUDA_CHECK(cudaEventRecord(e0, nullptr));
+            for (int i = 0; i < iters; ++i) gemm(cx, M, N, K, dA.as<float>(), K, l, dC.as<float>(), ldc, gelu != 0);
+            CUDA_CHECK(cudaEventRecord(e1, nullptr));
+            CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+            *avg_us = (double)ms * 1e3 / iters;
+            cudaEventDestroy(e0); cudaEventDestroy(e1);
+        }
+        CUDA_CHECK(cudaMemcpy2D(C, (size_t)N * 4, dC.p, (size_t)ldc * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost));
     });
 }
 

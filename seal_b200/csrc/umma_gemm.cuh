@@ -1,0 +1,204 @@
+// Blackwell-native GEMM for the BART decoder/encoder linears and the lm_head:
+//   C[M,N] = A[M,K] * W[N,K]^T + bias[N]   (optional exact GELU), fp32 in / fp32 out,
+// computed on the 5th-gen tensor cores as an error-compensated 3xTF32 product
+//   A*W ~= A_lo*W_hi + A_hi*W_lo + A_hi*W_hi,   x_hi = x with the 13 low mantissa bits cleared,
+//                                                x_lo = x - x_hi (exact),
+// which keeps the fp32-level accuracy the 1e-4 beam-score parity needs (a single TF32/BF16 pass
+// does not).  tcgen05.mma (kind::tf32, M=128, N=BN, K=8) issued by one thread, operands staged by
+// TMA into 128B-swizzled K-major shared-memory tiles, fp32 accumulators in TMEM, epilogue
+// tcgen05.ld -> registers -> global.  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM
+// allocator, 4..7 = epilogue.  One CTA per 128 x BN output tile.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sealb200 {
+
+constexpr int UM = 128;            // tile rows  (UMMA M)
+constexpr int UK = 32;             // k-block: 32 fp32 = 128 B = one swizzle row
+constexpr int USTAGES = 2;
+constexpr int UTHREADS = 256;
+
+template <int BN>
+struct UmmaSmem {
+    static constexpr int kABytes = UM * 128;        // one A tile (hi or lo)
+    static constexpr int kWBytes = BN * 128;
+    static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+    static constexpr int kTotal = USTAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must trap (error code back to the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp:SmemDescriptor):
+// start>>4 | LBO(1)<<16 | SBO(1024 B >> 4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_erf_u(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// x -> (hi, lo): hi keeps the TF32 bits (sign, exponent, 10 mantissa bits), lo = x - hi exactly.
+__global__ void __launch_bounds__(256) split_tf32_kernel(int64_t n4, const float4* __restrict__ x, float4* __restrict__ hi,
+                                                         float4* __restrict__ lo) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 h, l;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+        hi[i] = h; lo[i] = l;
+    }
+}
+
+template <int BN, bool GELU>
+__global__ void __launch_bounds__(UTHREADS, 1)
+umma_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                        const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                        int M, int N, int K, const float* __restrict__ bias, float* __restrict__ C, int ldc) {
+    using SM = UmmaSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024 B alignment
+    const uint32_t bars = base + USTAGES * SM::kStageBytes;               // full[USTAGES], empty[USTAGES], tmem_full, tmem slot
+    const uint32_t full0 = bars, empty0 = bars + 8 * USTAGES, tmem_full = bars + 16 * USTAGES, slot = tmem_full + 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.y, n_tile = blockIdx.x;
+    const int num_k = K / UK;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < USTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % USTAGES;
+                const uint32_t ph = (kb / USTAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t st = base + s * SM::kStageBytes;
+                mbar_expect_tx(full0 + 8 * s, SM::kStageBytes);
+                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UK, m_tile * UM);
+                tma_load_2d(st + SM::kABytes, &tmA_lo, full0 + 8 * s, kb * UK, m_tile * UM);
+                tma_load_2d(st + 2 * SM::kABytes, &tmW_hi, full0 + 8 * s, kb * UK, n_tile * BN);
+                tma_load_2d(st + 2 * SM::kABytes + SM::kWBytes, &tmW_lo, full0 + 8 * s, kb * UK, n_tile * BN);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute/arch/mma_sm100_desc.hpp:InstrDescriptor): D=F32, A=B=TF32, K-major both,
+            // N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % USTAGES;
+                const uint32_t ph = (kb / USTAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = base + s * SM::kStageBytes;
+                const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + SM::kABytes);
+                const uint64_t w_hi = umma_desc_sw128(st + 2 * SM::kABytes), w_lo = umma_desc_sw128(st + 2 * SM::kABytes + SM::kWBytes);
+#pragma unroll
+                for (int k = 0; k < UK / 8; ++k) {             // UMMA_K = 8 tf32 = 32 B -> +2 in the >>4 address field
+                    umma_tf32(tmem_base, a_lo + 2 * k, w_hi + 2 * k, idesc, (kb | k) != 0);
+                    umma_tf32(tmem_base, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                    umma_tf32(tmem_base, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
+                }
+                umma_commit(empty0 + 8 * s);                   // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full);                            // accumulator complete
+        }
+    } else if (warp >= 4) {
+        const int ew = warp - 4;                               // TMEM lanes 32*ew .. 32*ew+31
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int row = m_tile * UM + ew * 32 + lane;
+        float* crow = C + (int64_t)row * ldc;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, r);
+            const int nb = n_tile * BN + c0;
+            if (row < M && nb < N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int n = nb + j;
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        float x = __uint_as_float(r[j + u]) + ((bias && n + u < N) ? bias[n + u] : 0.f);
+                        v[u] = GELU ? gelu_erf_u(x) : x;
+                    }
+                    if (n + 3 < N) *reinterpret_cast<float4*>(crow + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    else for (int u = 0; u < 4; ++u) if (n + u < N) crow[n + u] = v[u];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+}  // namespace sealb200
