@@ -13,6 +13,7 @@ No CPU path: CPU tensors are rejected.
 """
 import ctypes as C
 import math
+import os
 import weakref
 from typing import List, Optional
 
@@ -92,7 +93,11 @@ class IndexBasedLogitsProcessor:
 class SealBartEngine:
     """Device-resident BART weights + workspace (include/sealdec.h `sealbart_t`)."""
 
-    def __init__(self, state_dict, config, device=0, gemm_mode=0):
+    def __init__(self, state_dict, config, device=0, gemm_mode=None):
+        # gemm_mode: 0 = fp32 SIMT kernel, 1 = 3xTF32 tcgen05/TMA kernel; $SEALB200_GEMM overrides the default
+        if gemm_mode is None:
+            gemm_mode = int(os.environ.get("SEALB200_GEMM", "0"))
+        self.gemm_mode = int(gemm_mode)
         d = int(config.d_model)
         self.config = config
         self.device = int(device)
@@ -117,7 +122,7 @@ class SealBartEngine:
         check(lib.sealbart_finalize(self._h))
 
     @classmethod
-    def from_hf(cls, model, device=None, gemm_mode=0):
+    def from_hf(cls, model, device=None, gemm_mode=None):
         torch = _torch()
         if device is None:
             p = next(model.parameters())

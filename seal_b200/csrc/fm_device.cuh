@@ -6,11 +6,12 @@
 //              past a node behave exactly as in the reference — SURVEY.md §H1) cut into 192-bit
 //              payloads with the absolute rank in front.  One rank query = ONE 32-byte sector
 //              (sdsl: 16 B of counts + 8 B of bits in two different arrays, rank_support_v.hpp:114-124).
-//   csym       u64[2^L + 1]: number of BWT symbols < c.  Doubles as the node-offset table: the node
-//              of prefix p at level k starts at csym[p << (L-k)] inside level k.
-//   node_ones  u64[2^L], heap order (index (1<<k)+p): rank1 at that node's first bit.  Removes the
-//              two node-boundary ranks sdsl performs per level (wt_int.hpp:365-367) — they are
-//              static per node.
+//   csym       u64[2^L + 1]: number of BWT symbols < c (C array over the dense symbol space).
+//   node_tab   {u64 base, u64 ones}[2^L], heap order (index (1<<k)+p): absolute bit position of the
+//              first bit of node (level k, prefix p) = k*m + csym[p << (L-k)], and rank1 there.
+//              Removes the two node-boundary ranks sdsl performs per level (wt_int.hpp:365-367) —
+//              they are static per node — and is one 16-byte load; the two children of a node sit
+//              in one 32-byte sector.
 //   sa_samples u64[ceil(m/32)], SA[32 i];   isa_samples u64[(m-1)/64+1], ISA[64 i]
 //
 // Everything here is per-thread code marked SEAL_HD so tests/hostcheck can compile the very same
@@ -28,10 +29,12 @@ struct uint4 { unsigned int x, y, z, w; };
 
 namespace sealb200 {
 
+struct NodeEntry { uint64_t base, ones; };
+
 struct FmView {
     const uint4* blocks;
     const uint64_t* csym;
-    const uint64_t* node_ones;
+    const NodeEntry* node_tab;
     const uint64_t* sa_samples;
     const uint64_t* isa_samples;
     const uint64_t* beginnings;     // optional (doc offsets), may be null
@@ -46,6 +49,18 @@ SEAL_HD int popc64(uint64_t x) {
     return __popcll(x);
 #else
     return __builtin_popcountll(x);
+#endif
+}
+
+SEAL_HD NodeEntry load_node(const FmView& v, uint32_t heap) {
+#if defined(__CUDA_ARCH__)
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(v.node_tab + heap));
+    NodeEntry e;
+    e.base = (static_cast<uint64_t>(q.y) << 32) | q.x;
+    e.ones = (static_cast<uint64_t>(q.w) << 32) | q.z;
+    return e;
+#else
+    return v.node_tab[heap];
 #endif
 }
 
@@ -79,15 +94,17 @@ SEAL_HD uint64_t rank1(const FmView& v, uint64_t p, int* bit = nullptr) {
 // for two positions at once so the two dependent load chains overlap.
 SEAL_HD void wt_rank2(const FmView& v, uint64_t i, uint64_t j, uint32_t c, uint64_t& ri, uint64_t& rj) {
     const uint32_t L = v.L;
+    NodeEntry e = load_node(v, 1);                          // root: base 0, ones 0
     for (uint32_t k = 0; k < L && (i | j); ++k) {
-        const uint32_t prefix = (k == 0) ? 0u : (c >> (L - k));
-        const uint64_t start = v.csym[static_cast<uint64_t>(prefix) << (L - k)];
-        const uint64_t o1 = v.node_ones[(1u << k) + prefix];
-        const uint64_t base = static_cast<uint64_t>(k) * v.m + start;
-        const uint64_t a = rank1(v, base + i) - o1;
-        const uint64_t b = rank1(v, base + j) - o1;
+        // the next node on c's path is known without looking at the data: fetch its entry now so
+        // that each level costs one dependent memory round trip (the rank sector), not two
+        NodeEntry nx = e;
+        if (k + 1 < L) nx = load_node(v, (2u << k) + (c >> (L - 1 - k)));
+        const uint64_t a = rank1(v, e.base + i) - e.ones;
+        const uint64_t b = rank1(v, e.base + j) - e.ones;
         if ((c >> (L - 1 - k)) & 1) { i = a; j = b; }
         else { i -= a; j -= b; }
+        e = nx;
     }
     ri = i; rj = j;
 }
@@ -116,10 +133,9 @@ SEAL_HD uint64_t inverse_select(const FmView& v, uint64_t i, uint32_t& c_out) {
     const uint32_t L = v.L;
     uint32_t prefix = 0;
     for (uint32_t k = 0; k < L; ++k) {
-        const uint64_t start = v.csym[static_cast<uint64_t>(prefix) << (L - k)];
-        const uint64_t o1 = v.node_ones[(1u << k) + prefix];
+        const NodeEntry e = load_node(v, (1u << k) + prefix);
         int bit;
-        const uint64_t a = rank1(v, static_cast<uint64_t>(k) * v.m + start + i, &bit) - o1;
+        const uint64_t a = rank1(v, e.base + i, &bit) - e.ones;
         i = bit ? a : i - a;
         prefix = (prefix << 1) | static_cast<uint32_t>(bit);
     }
@@ -184,30 +200,37 @@ SEAL_HD void extract_text(const FmView& v, uint64_t begin, uint64_t end, uint64_
 // node tables.  sink(symbol, rank_i, rank_j) is called in ascending symbol order.
 template <typename Sink>
 SEAL_HD void expand_dfs(const FmView& v, uint32_t level, uint32_t prefix, uint64_t i, uint64_t j, Sink& sink) {
-    struct Frame { uint64_t i, j; uint32_t prefix, level; };
+    struct Frame { uint64_t i, j; NodeEntry e; uint32_t prefix, level; };
     Frame stk[36];
     int sp = 0;
-    stk[sp++] = Frame{i, j, prefix, level};
     const uint32_t L = v.L;
+    {
+        NodeEntry e0{0, 0};
+        if (level < L) e0 = load_node(v, (1u << level) + prefix);
+        stk[sp++] = Frame{i, j, e0, prefix, level};
+    }
     while (sp) {
-        const Frame e = stk[--sp];
-        if (e.level == L) { sink(e.prefix, e.i, e.j); continue; }
-        const uint64_t start = v.csym[static_cast<uint64_t>(e.prefix) << (L - e.level)];
-        const uint64_t o1 = v.node_ones[(1u << e.level) + e.prefix];
-        const uint64_t base = static_cast<uint64_t>(e.level) * v.m + start;
+        const Frame f = stk[--sp];
+        if (f.level == L) { sink(f.prefix, f.i, f.j); continue; }
+        // children's table entries share one 32-byte sector; fetched together with the rank sectors
+        NodeEntry c0{0, 0}, c1{0, 0};
+        if (f.level + 1 < L) {
+            const uint32_t h = (2u << f.level) + 2u * f.prefix;
+            c0 = load_node(v, h); c1 = load_node(v, h + 1);
+        }
         uint64_t a, b;
-        if (e.j == e.i + 1) {                      // single position: one sector, take the bit
+        if (f.j == f.i + 1) {                      // single position: one sector, take the bit
             int bit;
-            a = rank1(v, base + e.i, &bit) - o1;
+            a = rank1(v, f.e.base + f.i, &bit) - f.e.ones;
             b = a + static_cast<uint64_t>(bit);
         } else {
-            a = rank1(v, base + e.i) - o1;
-            b = rank1(v, base + e.j) - o1;
+            a = rank1(v, f.e.base + f.i) - f.e.ones;
+            b = rank1(v, f.e.base + f.j) - f.e.ones;
         }
         const uint64_t ones = b - a;
-        const uint64_t zeros = (e.j - e.i) - ones;
-        if (ones) stk[sp++] = Frame{a, b, (e.prefix << 1) | 1u, e.level + 1};
-        if (zeros) stk[sp++] = Frame{e.i - a, e.j - b, e.prefix << 1, e.level + 1};
+        const uint64_t zeros = (f.j - f.i) - ones;
+        if (ones) stk[sp++] = Frame{a, b, c1, (f.prefix << 1) | 1u, f.level + 1};
+        if (zeros) stk[sp++] = Frame{f.i - a, f.j - b, c0, f.prefix << 1, f.level + 1};
     }
 }
 

@@ -45,9 +45,8 @@ __device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sin
         bool has0 = false, has1 = false;
         if (lane < n) {
             ei = F.i[cur][lane]; ej = F.j[cur][lane]; ep = F.prefix[cur][lane];
-            const uint64_t start = v.csym[static_cast<uint64_t>(ep) << (L - level)];
-            const uint64_t o1 = v.node_ones[(1u << level) + ep];
-            const uint64_t base = static_cast<uint64_t>(level) * v.m + start;
+            const NodeEntry ne = load_node(v, (1u << level) + ep);
+            const uint64_t base = ne.base, o1 = ne.ones;
             if (ej == ei + 1) {
                 int bit;
                 a = rank1(v, base + ei, &bit) - o1;

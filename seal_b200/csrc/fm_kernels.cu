@@ -28,7 +28,7 @@ struct sealfm {
     FmView view{};                 // device pointers
     void* d_blocks = nullptr;
     uint64_t* d_csym = nullptr;
-    uint64_t* d_node_ones = nullptr;
+    NodeEntry* d_node_tab = nullptr;
     uint64_t* d_sa = nullptr;
     uint64_t* d_isa = nullptr;
     uint64_t* d_beginnings = nullptr;
@@ -193,7 +193,7 @@ void upload(sealfm_t* h, int device) {
     make_device_arrays(H, A);
     const std::vector<uint64_t>& blk = A.blocks;
     const std::vector<uint64_t>& csym = A.csym;
-    const std::vector<uint64_t>& node_ones = A.node_ones;
+    const std::vector<NodeEntry>& node_tab = A.node_tab;
 
     auto put = [&](const void* src, uint64_t bytes) -> void* {
         void* d = nullptr;
@@ -205,12 +205,12 @@ void upload(sealfm_t* h, int device) {
     h->device_bytes = 0;
     h->d_blocks = put(blk.data(), blk.size() * 8);
     h->d_csym = (uint64_t*)put(csym.data(), csym.size() * 8);
-    h->d_node_ones = (uint64_t*)put(node_ones.data(), node_ones.size() * 8);
+    h->d_node_tab = (NodeEntry*)put(node_tab.data(), node_tab.size() * sizeof(NodeEntry));
     h->d_sa = (uint64_t*)put(H.sa_samples.data(), H.sa_samples.size() * 8);
     h->d_isa = (uint64_t*)put(H.isa_samples.data(), H.isa_samples.size() * 8);
     FmView& v = h->view;
     v.blocks = (const uint4*)h->d_blocks;
-    v.csym = h->d_csym; v.node_ones = h->d_node_ones;
+    v.csym = h->d_csym; v.node_tab = h->d_node_tab;
     v.sa_samples = h->d_sa; v.isa_samples = h->d_isa;
     v.n_isa = H.isa_samples.size();
     v.beginnings = nullptr; v.n_beginnings = 0;
@@ -225,7 +225,7 @@ void upload(sealfm_t* h, int device) {
 void release_device(sealfm_t* h) {
     if (h->device < 0) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_blocks); cudaFree(h->d_csym); cudaFree(h->d_node_ones);
+    cudaFree(h->d_blocks); cudaFree(h->d_csym); cudaFree(h->d_node_tab);
     cudaFree(h->d_sa); cudaFree(h->d_isa); cudaFree(h->d_beginnings);
     h->device = -1;
 }

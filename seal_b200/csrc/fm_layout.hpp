@@ -11,7 +11,7 @@ namespace sealb200 {
 struct DeviceArrays {
     std::vector<uint64_t> blocks;      // 4 u64 per 32-byte block
     std::vector<uint64_t> csym;        // 2^L + 1
-    std::vector<uint64_t> node_ones;   // 2^L, heap order
+    std::vector<NodeEntry> node_tab;   // 2^L, heap order
 };
 
 inline void make_device_arrays(const HostIndex& H, DeviceArrays& A) {
@@ -39,13 +39,15 @@ inline void make_device_arrays(const HostIndex& H, DeviceArrays& A) {
         while (a < H.sigma && H.alphabet[a] < c) ++a;
         A.csym[c] = a < H.sigma ? H.C[a] : m;
     }
-    A.node_ones.assign(nsym, 0);
+    A.node_tab.assign(nsym, NodeEntry{0, 0});
     FmView hv{};
     hv.blocks = reinterpret_cast<const uint4*>(A.blocks.data());
     hv.m = m; hv.L = L;
     for (uint32_t k = 0; k < L; ++k)
-        for (uint64_t p = 0; p < (1ULL << k); ++p)
-            A.node_ones[(1ULL << k) + p] = rank1(hv, static_cast<uint64_t>(k) * m + A.csym[p << (L - k)]);
+        for (uint64_t p = 0; p < (1ULL << k); ++p) {
+            const uint64_t base = static_cast<uint64_t>(k) * m + A.csym[p << (L - k)];
+            A.node_tab[(1ULL << k) + p] = NodeEntry{base, rank1(hv, base)};
+        }
 }
 
 }  // namespace sealb200

@@ -27,7 +27,7 @@ static void bind(HC* h) {
     make_device_arrays(h->H, h->A);
     h->v.blocks = reinterpret_cast<const uint4*>(h->A.blocks.data());
     h->v.csym = h->A.csym.data();
-    h->v.node_ones = h->A.node_ones.data();
+    h->v.node_tab = h->A.node_tab.data();
     h->v.sa_samples = h->H.sa_samples.data();
     h->v.isa_samples = h->H.isa_samples.data();
     h->v.n_isa = h->H.isa_samples.size();
