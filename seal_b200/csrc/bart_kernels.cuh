@@ -22,12 +22,22 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// TF32 split used by the tcgen05 GEMM (umma_gemm.cuh): hi keeps sign/exponent/10 mantissa bits,
+// lo = x - hi exactly.  Producers write the split directly so no separate pass is needed.
+__device__ __forceinline__ void split1(float x, float& h, float& l) {
+    h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    l = x - h;
+}
+__device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
+    split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
+}
+
 // LayerNorm of one row held as `per` float4 per lane (d = 128*per), torch semantics:
 // biased variance, eps inside the sqrt, fp32.
 template <int MAXV>
 __device__ __forceinline__ void warp_layernorm(float4 (&v)[MAXV], int nv, int d, const float* __restrict__ gamma,
                                                const float* __restrict__ beta, float eps, float* __restrict__ out,
-                                               int lane) {
+                                               float* __restrict__ out_hi, float* __restrict__ out_lo, int lane) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -49,7 +59,13 @@ __device__ __forceinline__ void warp_layernorm(float4 (&v)[MAXV], int nv, int d,
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
-        *reinterpret_cast<float4*>(out + col) = o;
+        if (out) *reinterpret_cast<float4*>(out + col) = o;
+        if (out_hi) {
+            float4 h, l;
+            split4(o, h, l);
+            *reinterpret_cast<float4*>(out_hi + col) = h;
+            *reinterpret_cast<float4*>(out_lo + col) = l;
+        }
     }
 }
 
@@ -63,7 +79,8 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
                                                        const float* __restrict__ embed, float scale,
                                                        const float* __restrict__ pos_table,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float* __restrict__ out) {
+                                                       float* __restrict__ out, float* __restrict__ out_hi,
+                                                       float* __restrict__ out_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -79,13 +96,15 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
         const float4 b = *reinterpret_cast<const float4*>(pe + col);
         v[i] = make_float4(a.x * scale + b.x, a.y * scale + b.y, a.z * scale + b.z, a.w * scale + b.w);
     }
-    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out + r * d, lane);
+    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out ? out + r * d : nullptr,
+                              out_hi ? out_hi + r * d : nullptr, out_lo ? out_lo + r * d : nullptr, lane);
 }
 
 // out[r] = LN(a[r] + b[r])     (residual + sub-layer output, post-LN)
 __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                      const float* __restrict__ b, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ out) {
+                                                     const float* __restrict__ beta, float* __restrict__ out,
+                                                     float* __restrict__ out_hi, float* __restrict__ out_lo) {
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -98,7 +117,8 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
         const float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
         v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
     }
-    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out + r * d, lane);
+    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out ? out + r * d : nullptr,
+                              out_hi ? out_hi + r * d : nullptr, out_lo ? out_lo + r * d : nullptr, lane);
 }
 
 // ---- fp32 SIMT GEMM:  C[M,N] = A[M,K] * W[N,K]^T + bias[N]  (optionally GELU) ---------------------
@@ -188,94 +208,147 @@ __global__ void __launch_bounds__(GTHREADS, 2) sgemm_tn_kernel(int M, int N, int
 }
 
 // ---- attention ---------------------------------------------------------------------------------
-// One warp per (row, head); lane holds dims {2*lane, 2*lane+1} of the 64-wide head.
-// Online softmax (running max / sum) in fp32; scores scaled by head_dim^-0.5 = 0.125.
-
-struct OnlineSoftmax {
-    float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
-    __device__ __forceinline__ void push(float s, float vx, float vy) {
-        const float mn = fmaxf(m, s);
-        const float c = (m == -INFINITY) ? 0.f : expf(m - mn);
-        const float p = expf(s - mn);
-        l = l * c + p; ax = ax * c + p * vx; ay = ay * c + p * vy; m = mn;
+// One warp per (row, head).  Scores: lane s owns key s (its own 256-byte K row against the query
+// staged in shared memory) -> two warp reductions per 32 keys instead of one per key; values: lane l
+// owns dims {2l, 2l+1} and accumulates p_s * V[s] with the probabilities broadcast by shuffle.
+// fp32 throughout; scores scaled by head_dim^-0.5 = 0.125; chunks of 32 keys merged online.
+template <typename KV>
+__device__ __forceinline__ float2 warp_attend(const float* __restrict__ q_head, int n_keys, const KV& kv,
+                                              float* __restrict__ q_s) {
+    const int lane = threadIdx.x & 31;
+    {
+        const float2 q2 = *reinterpret_cast<const float2*>(q_head + 2 * lane);
+        q_s[2 * lane] = q2.x; q_s[2 * lane + 1] = q2.y;
     }
-};
+    __syncwarp();
+    float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
+    for (int s0 = 0; s0 < n_keys; s0 += 32) {
+        const int s = s0 + lane;
+        const bool ok = s < n_keys && kv.valid(s);
+        float sc = -INFINITY;
+        if (ok) {
+            const float4* kp = reinterpret_cast<const float4*>(kv.k(s));
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < kHeadDim / 4; ++i) {
+                const float4 kk = kp[i];
+                const float4 qq = *reinterpret_cast<const float4*>(q_s + 4 * i);
+                acc = fmaf(qq.x, kk.x, acc); acc = fmaf(qq.y, kk.y, acc); acc = fmaf(qq.z, kk.z, acc); acc = fmaf(qq.w, kk.w, acc);
+            }
+            sc = acc * 0.125f;
+        }
+        const float mn = fmaxf(m, warp_max(sc));
+        if (mn == -INFINITY) continue;                         // every key so far is masked (warp-uniform)
+        const float p = ok ? expf(sc - mn) : 0.f;
+        const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+        l = l * corr + warp_sum(p);
+        ax *= corr; ay *= corr;
+        const int cnt = n_keys - s0 < 32 ? n_keys - s0 : 32;
+        for (int j = 0; j < cnt; ++j) {
+            const float pj = __shfl_sync(0xffffffffu, p, j);
+            if (pj != 0.f) {                                   // warp-uniform
+                const float2 vv = *reinterpret_cast<const float2*>(kv.v(s0 + j) + 2 * lane);
+                ax = fmaf(pj, vv.x, ax); ay = fmaf(pj, vv.y, ay);
+            }
+        }
+        m = mn;
+    }
+    __syncwarp();
+    return make_float2(ax / l, ay / l);
+}
+
+__device__ __forceinline__ void store_attn(float2 o, int64_t idx, float* __restrict__ out, float* __restrict__ out_hi,
+                                           float* __restrict__ out_lo) {
+    if (out) *reinterpret_cast<float2*>(out + idx) = o;
+    if (out_hi) {
+        float2 h, l;
+        split1(o.x, h.x, l.x); split1(o.y, h.y, l.y);
+        *reinterpret_cast<float2*>(out_hi + idx) = h;
+        *reinterpret_cast<float2*>(out_lo + idx) = l;
+    }
+}
 
 // Decoder self-attention for one new token per row with beam-ancestry indirection instead of a
 // cache reorder (the reference index_selects 24 cache tensors per step, seal/beam_search.py:331-332).
 // qkv: [R][3d] (q | k | v) of the current position; kc/vc: [T][R][d] per layer; anc: [R][T] source row
-// of every earlier position.  Writes this position's k,v into the cache.
-__global__ void __launch_bounds__(512) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
-                                                            const float* __restrict__ qkv, float* __restrict__ kc,
-                                                            float* __restrict__ vc, const int32_t* __restrict__ anc,
-                                                            float* __restrict__ out) {
+// of every earlier position.  Writes this position's k,v into the cache first.
+struct SelfKV {
+    const float* kc; const float* vc; const int32_t* anc; const float* cur_k; const float* cur_v;
+    int64_t R; int d, col0, cur_pos;
+    __device__ __forceinline__ bool valid(int) const { return true; }
+    // the current position's k/v are read from this step's qkv, never back from the cache just written
+    __device__ __forceinline__ const float* k(int s) const {
+        return s == cur_pos ? cur_k : kc + ((int64_t)s * R + anc[s]) * d + col0;
+    }
+    __device__ __forceinline__ const float* v(int s) const {
+        return s == cur_pos ? cur_v : vc + ((int64_t)s * R + anc[s]) * d + col0;
+    }
+};
+__global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
+                                                            const float* __restrict__ qkv, float* kc, float* vc,
+                                                            const int32_t* __restrict__ anc,
+                                                            float* __restrict__ out, float* __restrict__ out_hi,
+                                                            float* __restrict__ out_lo) {
+    __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t r = blockIdx.x;
-    const int lane = threadIdx.x & 31;
-    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = warp; h < heads; h += blockDim.x >> 5) {
         const int col = h * kHeadDim + lane * 2;
-        const float2 q = *reinterpret_cast<const float2*>(qkv + r * 3 * d + col);
         const float2 k = *reinterpret_cast<const float2*>(qkv + r * 3 * d + d + col);
         const float2 v = *reinterpret_cast<const float2*>(qkv + r * 3 * d + 2 * d + col);
         *reinterpret_cast<float2*>(kc + ((int64_t)cur_pos * R + r) * d + col) = k;
         *reinterpret_cast<float2*>(vc + ((int64_t)cur_pos * R + r) * d + col) = v;
-        OnlineSoftmax sm;
-        for (int s = 0; s < cur_pos; ++s) {
-            const int64_t src = anc[r * T + s];
-            const float2 ks = *reinterpret_cast<const float2*>(kc + ((int64_t)s * R + src) * d + col);
-            const float2 vs = *reinterpret_cast<const float2*>(vc + ((int64_t)s * R + src) * d + col);
-            const float sc = warp_sum(q.x * ks.x + q.y * ks.y) * 0.125f;
-            sm.push(sc, vs.x, vs.y);
-        }
-        const float sc = warp_sum(q.x * k.x + q.y * k.y) * 0.125f;
-        sm.push(sc, v.x, v.y);
-        *reinterpret_cast<float2*>(out + r * d + col) = make_float2(sm.ax / sm.l, sm.ay / sm.l);
+        SelfKV kv{kc, vc, anc + r * T, qkv + r * 3 * d + d + h * kHeadDim, qkv + r * 3 * d + 2 * d + h * kHeadDim,
+                  R, d, h * kHeadDim, cur_pos};
+        const float2 o = warp_attend(qkv + r * 3 * d + h * kHeadDim, cur_pos + 1, kv, q_s[warp]);
+        store_attn(o, r * d + col, out, out_hi, out_lo);
     }
 }
 
 // Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states; row r belongs to query
 // r / beams.  Padded source positions (mask == 0) are excluded.
-__global__ void __launch_bounds__(512) cross_attn_kernel(int64_t R, int d, int heads, int beams, int S,
+struct CrossKV {
+    const float* base; const int32_t* mask; int d, col0;
+    __device__ __forceinline__ bool valid(int s) const { return mask[s] != 0; }
+    __device__ __forceinline__ const float* k(int s) const { return base + (int64_t)s * 2 * d + col0; }
+    __device__ __forceinline__ const float* v(int s) const { return base + (int64_t)s * 2 * d + d + col0; }
+};
+__global__ void __launch_bounds__(512, 2) cross_attn_kernel(int64_t R, int d, int heads, int beams, int S,
                                                          const float* __restrict__ q, const float* __restrict__ ckv,
-                                                         const int32_t* __restrict__ src_mask, float* __restrict__ out) {
+                                                         const int32_t* __restrict__ src_mask, float* __restrict__ out,
+                                                         float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t r = blockIdx.x;
     const int64_t qi = r / beams;
-    const int lane = threadIdx.x & 31;
-    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
-        const int col = h * kHeadDim + lane * 2;
-        const float2 qq = *reinterpret_cast<const float2*>(q + r * d + col);
-        OnlineSoftmax sm;
-        for (int s = 0; s < S; ++s) {
-            if (!src_mask[qi * S + s]) continue;
-            const float* base = ckv + (qi * S + s) * 2 * d;
-            const float2 ks = *reinterpret_cast<const float2*>(base + col);
-            const float2 vs = *reinterpret_cast<const float2*>(base + d + col);
-            sm.push(warp_sum(qq.x * ks.x + qq.y * ks.y) * 0.125f, vs.x, vs.y);
-        }
-        *reinterpret_cast<float2*>(out + r * d + col) = make_float2(sm.ax / sm.l, sm.ay / sm.l);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = warp; h < heads; h += blockDim.x >> 5) {
+        CrossKV kv{ckv + qi * S * 2 * d, src_mask + qi * S, d, h * kHeadDim};
+        const float2 o = warp_attend(q + r * d + h * kHeadDim, S, kv, q_s[warp]);
+        store_attn(o, r * d + h * kHeadDim + lane * 2, out, out_hi, out_lo);
     }
 }
 
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).
 // qkv [Q*S][3d].
-__global__ void __launch_bounds__(512) enc_self_attn_kernel(int64_t tokens, int d, int heads, int S,
+struct EncKV {
+    const float* base; const int32_t* mask; int d, col0;
+    __device__ __forceinline__ bool valid(int s) const { return mask[s] != 0; }
+    __device__ __forceinline__ const float* k(int s) const { return base + (int64_t)s * 3 * d + d + col0; }
+    __device__ __forceinline__ const float* v(int s) const { return base + (int64_t)s * 3 * d + 2 * d + col0; }
+};
+__global__ void __launch_bounds__(512, 2) enc_self_attn_kernel(int64_t tokens, int d, int heads, int S,
                                                             const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ src_mask,
-                                                            float* __restrict__ out) {
+                                                            float* __restrict__ out, float* __restrict__ out_hi,
+                                                            float* __restrict__ out_lo) {
+    __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t t = blockIdx.x;
     const int64_t qi = t / S;
-    const int lane = threadIdx.x & 31;
-    for (int h = threadIdx.x >> 5; h < heads; h += blockDim.x >> 5) {
-        const int col = h * kHeadDim + lane * 2;
-        const float2 qq = *reinterpret_cast<const float2*>(qkv + t * 3 * d + col);
-        OnlineSoftmax sm;
-        for (int s = 0; s < S; ++s) {
-            if (!src_mask[qi * S + s]) continue;
-            const float* base = qkv + (qi * S + s) * 3 * d;
-            const float2 ks = *reinterpret_cast<const float2*>(base + d + col);
-            const float2 vs = *reinterpret_cast<const float2*>(base + 2 * d + col);
-            sm.push(warp_sum(qq.x * ks.x + qq.y * ks.y) * 0.125f, vs.x, vs.y);
-        }
-        *reinterpret_cast<float2*>(out + t * d + col) = make_float2(sm.ax / sm.l, sm.ay / sm.l);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int h = warp; h < heads; h += blockDim.x >> 5) {
+        EncKV kv{qkv + qi * S * 3 * d, src_mask + qi * S, d, h * kHeadDim};
+        const float2 o = warp_attend(qkv + t * 3 * d + h * kHeadDim, S, kv, q_s[warp]);
+        store_attn(o, t * d + h * kHeadDim + lane * 2, out, out_hi, out_lo);
     }
 }
 

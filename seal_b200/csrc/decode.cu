@@ -63,6 +63,7 @@ struct sealbart {
     // workspace
     Buf enc_tok, enc_mask, ex, eqkv, eattn, etmp, effn, ckv;
     Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
+    Buf ex_hi, ex_lo, eattn_hi, eattn_lo, effn_hi, effn_lo, dx_hi, dx_lo, dattn_hi, dattn_lo, dffn_hi, dffn_lo;   // TF32 splits (gemm_mode 1)
     Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
     Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo;
     std::vector<void*> split_allocs;
@@ -177,27 +178,35 @@ void split_into(cudaStream_t s, const float* x, float* hi, float* lo, uint64_t n
     CUDA_CHECK(cudaGetLastError());
 }
 
+// An activation tensor as the GEMMs see it: plain fp32 and/or its TF32 split (hi, lo).
+struct Act { float* x = nullptr; float* hi = nullptr; float* lo = nullptr; };
+
 void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& whi,
-                 const CUtensorMap& wlo, const float* bias, float* C, int ldc, bool gelu) {
+                 const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu) {
     using SMm = UmmaSmem<kUmmaBN>;
     dim3 grid((N + kUmmaBN - 1) / kUmmaBN, (unsigned)((M + UM - 1) / UM));
     if (gelu) {
         CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-        umma_gemm_tf32x3_kernel<kUmmaBN, true><<<grid, UTHREADS, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C, ldc);
+        umma_gemm_tf32x3_kernel<kUmmaBN, true><<<grid, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
     } else {
         CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-        umma_gemm_tf32x3_kernel<kUmmaBN, false><<<grid, UTHREADS, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C, ldc);
+        umma_gemm_tf32x3_kernel<kUmmaBN, false><<<grid, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
     }
     CUDA_CHECK(cudaGetLastError());
 }
 
-void gemm(Ctx& cx, int64_t M, int N, int K, const float* A, int lda, Lin& l, float* C, int ldc, bool gelu) {
+// C = A W^T + b (+GELU).  gemm_mode 1: 3xTF32 tcgen05 kernel on the pre-split operands (A.hi/A.lo
+// written by the producing kernel; split here only if the producer did not).  gemm_mode 0: fp32 SIMT.
+void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
     if (M == 0) return;
     sealbart* m = cx.m;
     if (m->cfg.gemm_mode == 1 && K % UK == 0 && lda == K && l.w_hi) {
-        // 3xTF32 on tcgen05: split the activations, weights were split once at finalize
-        float* ahi = m->a_hi.as<float>(); float* alo = m->a_lo.as<float>();
-        split_into(cx.s, A, ahi, alo, (uint64_t)M * K); m->launches++;
+        const float* ahi = A.hi; const float* alo = A.lo;
+        if (!ahi) {
+            m->a_hi.ensure((size_t)M * K * 4); m->a_lo.ensure((size_t)M * K * 4);
+            split_into(cx.s, A.x, m->a_hi.as<float>(), m->a_lo.as<float>(), (uint64_t)M * K); m->launches++;
+            ahi = m->a_hi.as<float>(); alo = m->a_lo.as<float>();
+        }
         CUtensorMap mah, mal;
         make_map(&mah, ahi, M, K, K, UM); make_map(&mal, alo, M, K, K, UM);
         if (!l.maps_ready) { make_map(&l.map_hi, l.w_hi, N, K, K, kUmmaBN); make_map(&l.map_lo, l.w_lo, N, K, K, kUmmaBN); l.maps_ready = true; }
@@ -206,15 +215,16 @@ void gemm(Ctx& cx, int64_t M, int N, int K, const float* A, int lda, Lin& l, flo
         return;
     }
     if (K % GBK) throw ApiError(SEALFM_EINVAL, "GEMM K must be a multiple of 16");
+    if (!A.x || !C.x) throw ApiError(SEALFM_EINVAL, "internal: fp32 GEMM needs plain operands");
     dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
-    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, l.w, K, l.b, C, ldc);
-    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A, lda, l.w, K, l.b, C, ldc);
+    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A.x, lda, l.w, K, l.b, C.x, ldc);
+    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A.x, lda, l.w, K, l.b, C.x, ldc);
     CUDA_CHECK(cudaGetLastError());
     cx.m->launches++;
 }
 
-void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, float* out) {
-    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out);
+void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
+    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out.x, out.hi, out.lo);
     CUDA_CHECK(cudaGetLastError());
     cx.m->launches++;
 }
@@ -262,8 +272,12 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_lo.ensure(2 * D.R * 8); m->st_hi.ensure(2 * D.R * 8); m->st_pw.ensure(2 * D.R * 8);
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
     if (m->cfg.gemm_mode == 1) {
-        const size_t mx = (size_t)std::max<int64_t>(Tk, D.R) * std::max(D.f, D.d) * 4;
-        m->a_hi.ensure(mx); m->a_lo.ensure(mx);
+        m->ex_hi.ensure(Tk * D.d * 4); m->ex_lo.ensure(Tk * D.d * 4);
+        m->eattn_hi.ensure(Tk * D.d * 4); m->eattn_lo.ensure(Tk * D.d * 4);
+        m->effn_hi.ensure(Tk * D.f * 4); m->effn_lo.ensure(Tk * D.f * 4);
+        m->dx_hi.ensure(D.R * D.d * 4); m->dx_lo.ensure(D.R * D.d * 4);
+        m->dattn_hi.ensure(D.R * D.d * 4); m->dattn_lo.ensure(D.R * D.d * 4);
+        m->dffn_hi.ensure(D.R * D.f * 4); m->dffn_lo.ensure(D.R * D.f * 4);
     }
     m->err.ensure(4);
 }
@@ -275,27 +289,31 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     int32_t* tok = m->enc_tok.as<int32_t>(); int32_t* pos = tok + Tk; int32_t* m32 = m->enc_mask.as<int32_t>();
     prep_enc_kernel<<<(unsigned)((Tk + 255) / 256), 256, 0, cx.s>>>(Tk, (int)D.S, ids_d, mask_d, tok, m32, pos);
     CUDA_CHECK(cudaGetLastError()); m->launches++;
-    float* x = m->ex.as<float>(); float* qkv = m->eqkv.as<float>(); float* attn = m->eattn.as<float>();
-    float* tmp = m->etmp.as<float>(); float* ffn = m->effn.as<float>();
+    const bool sp = m->cfg.gemm_mode == 1;
+    const Act x{m->ex.as<float>(), sp ? m->ex_hi.as<float>() : nullptr, sp ? m->ex_lo.as<float>() : nullptr};
+    const Act qkv{m->eqkv.as<float>()};
+    const Act attn{sp ? nullptr : m->eattn.as<float>(), sp ? m->eattn_hi.as<float>() : nullptr, sp ? m->eattn_lo.as<float>() : nullptr};
+    const Act tmp{m->etmp.as<float>()};
+    const Act ffn{sp ? nullptr : m->effn.as<float>(), sp ? m->effn_hi.as<float>() : nullptr, sp ? m->effn_lo.as<float>() : nullptr};
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
     embed_ln_kernel<<<(unsigned)((Tk + 3) / 4), 128, 0, cx.s>>>(Tk, d, tok, 1, pos, 0, m->shared, scale, m->enc_pos,
-                                                                m->enc_ln_emb.g, m->enc_ln_emb.b, x);
+                                                                m->enc_ln_emb.g, m->enc_ln_emb.b, x.x, x.hi, x.lo);
     CUDA_CHECK(cudaGetLastError()); m->launches++;
     const int heads = m->cfg.heads;
     for (auto& L : m->enc) {
         gemm(cx, Tk, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        enc_self_attn_kernel<<<(unsigned)Tk, 32 * std::min(heads, 16), 0, cx.s>>>(Tk, d, heads, (int)D.S, qkv, m32, attn);
+        enc_self_attn_kernel<<<(unsigned)Tk, 32 * std::min(heads, 16), 0, cx.s>>>(Tk, d, heads, (int)D.S, qkv.x, m32, attn.x, attn.hi, attn.lo);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, Tk, d, d, attn, d, L.o, tmp, d, false);
-        add_ln(cx, Tk, d, x, tmp, L.ln_attn, x);
+        add_ln(cx, Tk, d, x.x, tmp.x, L.ln_attn, x);
         gemm(cx, Tk, D.f, d, x, d, L.fc1, ffn, D.f, true);
         gemm(cx, Tk, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
-        add_ln(cx, Tk, d, x, tmp, L.ln_final, x);
+        add_ln(cx, Tk, d, x.x, tmp.x, L.ln_final, x);
     }
     // per-query cross-attention K/V of every decoder layer, once (the reference recomputes nothing
     // either: HF caches them after the first step)
     for (int l = 0; l < m->cfg.decoder_layers; ++l)
-        gemm(cx, Tk, 2 * d, d, x, d, m->dec[l].ckv, m->ckv.as<float>() + (size_t)l * Tk * 2 * d, 2 * d, false);
+        gemm(cx, Tk, 2 * d, d, x, d, m->dec[l].ckv, Act{m->ckv.as<float>() + (size_t)l * Tk * 2 * d}, 2 * d, false);
 }
 
 // one decoder step for all R rows: token at position pos = cur_len-1 -> logits [R][ld]
@@ -304,11 +322,16 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     sealbart* m = cx.m;
     const int d = D.d; const int64_t R = D.R; const int64_t Tk = D.Q * D.S;
     const int pos = cur_len - 1;
-    float* x = m->dx.as<float>(); float* qkv = m->dqkv.as<float>(); float* attn = m->dattn.as<float>();
-    float* tmp = m->dtmp.as<float>(); float* cq = m->dcq.as<float>(); float* ffn = m->dffn.as<float>();
+    const bool sp = m->cfg.gemm_mode == 1;
+    const Act x{m->dx.as<float>(), sp ? m->dx_hi.as<float>() : nullptr, sp ? m->dx_lo.as<float>() : nullptr};
+    const Act qkv{m->dqkv.as<float>()};
+    const Act attn{sp ? nullptr : m->dattn.as<float>(), sp ? m->dattn_hi.as<float>() : nullptr, sp ? m->dattn_lo.as<float>() : nullptr};
+    const Act tmp{m->dtmp.as<float>()};
+    const Act cq{m->dcq.as<float>()};
+    const Act ffn{sp ? nullptr : m->dffn.as<float>(), sp ? m->dffn_hi.as<float>() : nullptr, sp ? m->dffn_lo.as<float>() : nullptr};
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
     embed_ln_kernel<<<(unsigned)((R + 3) / 4), 128, 0, cx.s>>>(R, d, tokens + pos, D.T, nullptr, pos, m->shared, scale,
-                                                               m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x);
+                                                               m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x.x, x.hi, x.lo);
     CUDA_CHECK(cudaGetLastError()); m->launches++;
     const int heads = m->cfg.heads;
     const int32_t* m32 = m->enc_mask.as<int32_t>();
@@ -317,24 +340,24 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         float* kc = m->kc.as<float>() + (size_t)l * D.T * R * d;
         float* vc = m->vc.as<float>() + (size_t)l * D.T * R * d;
         gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        dec_self_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv, kc, vc, anc, attn);
+        dec_self_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                               attn.x, attn.hi, attn.lo);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
-        add_ln(cx, R, d, x, tmp, L.ln_self, x);
+        add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
-        cross_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, D.B, (int)D.S, cq,
-                                                                            m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32, attn);
+        cross_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, D.B, (int)D.S, cq.x,
+                                                                            m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
+                                                                            attn.x, attn.hi, attn.lo);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
-        add_ln(cx, R, d, x, tmp, L.ln_cross, x);
+        add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
         gemm(cx, R, D.f, d, x, d, L.fc1, ffn, D.f, true);
         gemm(cx, R, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
-        add_ln(cx, R, d, x, tmp, L.ln_final, x);
+        add_ln(cx, R, d, x.x, tmp.x, L.ln_final, x);
     }
     if (ev_layers_done) CUDA_CHECK(cudaEventRecord(ev_layers_done, cx.s));
-    if (want_logits) {
-        gemm(cx, R, D.V, d, x, d, m->head, m->logits.as<float>(), D.ld, false);
-    }
+    if (want_logits) gemm(cx, R, D.V, d, x, d, m->head, Act{m->logits.as<float>()}, D.ld, false);
 }
 
 void check_model(const sealbart* m) {
@@ -386,7 +409,9 @@ void sealbart_free(sealbart_t* m) {
     for (Buf* b : {&m->enc_tok, &m->enc_mask, &m->ex, &m->eqkv, &m->eattn, &m->etmp, &m->effn, &m->ckv, &m->dx, &m->dqkv,
                    &m->dattn, &m->dtmp, &m->dcq, &m->dffn, &m->logits, &m->kc, &m->vc, &m->st_scores, &m->st_tokens,
                    &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->hy_score, &m->hy_len, &m->hy_tok,
-                   &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms, &m->a_hi, &m->a_lo})
+                   &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms, &m->a_hi, &m->a_lo, &m->ex_hi, &m->ex_lo,
+                   &m->eattn_hi, &m->eattn_lo, &m->effn_hi, &m->effn_lo, &m->dx_hi, &m->dx_lo, &m->dattn_hi, &m->dattn_lo,
+                   &m->dffn_hi, &m->dffn_lo})
         b->release();
     for (auto e : m->events) cudaEventDestroy(e);
     delete m;
@@ -651,15 +676,14 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
             split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);
-            fake.a_hi.ensure((size_t)M * K * 4); fake.a_lo.ensure((size_t)M * K * 4);
         }
         Ctx cx{&fake, nullptr};
-        gemm(cx, M, N, K, dA.as<float>(), K, l, dC.as<float>(), ldc, gelu != 0);
+        gemm(cx, M, N, K, Act{dA.as<float>()}, K, l, Act{dC.as<float>()}, ldc, gelu != 0);
         CUDA_CHECK(cudaDeviceSynchronize());
         if (iters > 0 && avg_us) {
             cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
             CUDA_CHECK(cudaEventRecord(e0, nullptr));
-            for (int i = 0; i < iters; ++i) gemm(cx, M, N, K, dA.as<float>(), K, l, dC.as<float>(), ldc, gelu != 0);
+            for (int i = 0; i < iters; ++i) gemm(cx, M, N, K, Act{dA.as<float>()}, K, l, Act{dC.as<float>()}, ldc, gelu != 0);
             CUDA_CHECK(cudaEventRecord(e1, nullptr));
             CUDA_CHECK(cudaEventSynchronize(e1));
             float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
