@@ -305,51 +305,102 @@ __global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d,
     }
 }
 
-// Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states; row r belongs to query
-// r / beams.  Padded source positions (mask == 0) are excluded.
-struct CrossKV {
-    const float* base; const int32_t* mask; int d, col0;
-    __device__ __forceinline__ bool valid(int s) const { return mask[s] != 0; }
-    __device__ __forceinline__ const float* k(int s) const { return base + (int64_t)s * 2 * d + col0; }
-    __device__ __forceinline__ const float* v(int s) const { return base + (int64_t)s * 2 * d + d + col0; }
+// Grouped attention: the `rows` query rows of group g (the beams of one query for cross attention,
+// the tokens of one query for the encoder) all attend to the same n_keys keys, so one CTA per
+// (group, head) stages each 32-key K/V chunk in shared memory ONCE and every warp reuses it
+// (the per-row version re-read K/V from L2 for each of the 15 beams: 3.4 GB per launch at R = 15 000).
+// K chunk is stored transposed+padded (lane = key reads conflict-free), V row-major (lane = dims).
+struct GroupAddr {
+    const float* q; int64_t q_stride;        // query row r of the group: q + r * q_stride (+ head offset)
+    const float* k; const float* v; int64_t kv_stride;   // key s: k + s * kv_stride (+ head offset)
+    const int32_t* mask;                     // [n_keys], 0 = padded key
 };
-__global__ void __launch_bounds__(512, 2) cross_attn_kernel(int64_t R, int d, int heads, int beams, int S,
-                                                         const float* __restrict__ q, const float* __restrict__ ckv,
-                                                         const int32_t* __restrict__ src_mask, float* __restrict__ out,
-                                                         float* __restrict__ out_hi, float* __restrict__ out_lo) {
+
+__device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, int n_keys, int head_off, int64_t out_base,
+                                                  int64_t out_stride, float* __restrict__ out, float* __restrict__ out_hi,
+                                                  float* __restrict__ out_lo) {
+    __shared__ float Kt[kHeadDim][33];
+    __shared__ __align__(16) float Vs[32][kHeadDim];
     __shared__ __align__(16) float q_s[16][kHeadDim];
-    const int64_t r = blockIdx.x;
-    const int64_t qi = r / beams;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int h = warp; h < heads; h += blockDim.x >> 5) {
-        CrossKV kv{ckv + qi * S * 2 * d, src_mask + qi * S, d, h * kHeadDim};
-        const float2 o = warp_attend(q + r * d + h * kHeadDim, S, kv, q_s[warp]);
-        store_attn(o, r * d + h * kHeadDim + lane * 2, out, out_hi, out_lo);
+    __shared__ int32_t valid_s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int r0 = 0; r0 < rows; r0 += nw) {                    // a pass handles nw query rows
+        const int r = r0 + warp;
+        const bool has_row = r < rows;
+        if (has_row) {
+            const float2 q2 = *reinterpret_cast<const float2*>(g.q + r * g.q_stride + head_off + 2 * lane);
+            q_s[warp][2 * lane] = q2.x; q_s[warp][2 * lane + 1] = q2.y;
+        }
+        float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
+        for (int s0 = 0; s0 < n_keys; s0 += 32) {
+            __syncthreads();                                   // previous chunk fully consumed
+            for (int e = threadIdx.x; e < 32 * (kHeadDim / 4); e += blockDim.x) {
+                const int s = e / (kHeadDim / 4), i4 = e % (kHeadDim / 4);
+                float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+                if (s0 + s < n_keys) {
+                    kk = *reinterpret_cast<const float4*>(g.k + (int64_t)(s0 + s) * g.kv_stride + head_off + 4 * i4);
+                    vv = *reinterpret_cast<const float4*>(g.v + (int64_t)(s0 + s) * g.kv_stride + head_off + 4 * i4);
+                }
+                Kt[4 * i4 + 0][s] = kk.x; Kt[4 * i4 + 1][s] = kk.y; Kt[4 * i4 + 2][s] = kk.z; Kt[4 * i4 + 3][s] = kk.w;
+                *reinterpret_cast<float4*>(&Vs[s][4 * i4]) = vv;
+            }
+            if (threadIdx.x < 32) valid_s[threadIdx.x] = (s0 + threadIdx.x < n_keys) && g.mask[s0 + threadIdx.x] != 0;
+            __syncthreads();
+            if (has_row) {
+                const bool ok = valid_s[lane] != 0;
+                float sc = -INFINITY;
+                if (ok) {
+                    float acc = 0.f;
+#pragma unroll 16
+                    for (int i = 0; i < kHeadDim; ++i) acc = fmaf(q_s[warp][i], Kt[i][lane], acc);
+                    sc = acc * 0.125f;
+                }
+                const float mn = fmaxf(m, warp_max(sc));
+                if (mn != -INFINITY) {
+                    const float p = ok ? expf(sc - mn) : 0.f;
+                    const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+                    l = l * corr + warp_sum(p);
+                    ax *= corr; ay *= corr;
+                    const int cnt = n_keys - s0 < 32 ? n_keys - s0 : 32;
+                    for (int j = 0; j < cnt; ++j) {
+                        const float pj = __shfl_sync(0xffffffffu, p, j);
+                        if (pj != 0.f) {
+                            const float2 vv = *reinterpret_cast<const float2*>(&Vs[j][2 * lane]);
+                            ax = fmaf(pj, vv.x, ax); ay = fmaf(pj, vv.y, ay);
+                        }
+                    }
+                    m = mn;
+                }
+            }
+        }
+        if (has_row) store_attn(make_float2(ax / l, ay / l), out_base + r * out_stride + head_off + 2 * lane, out, out_hi, out_lo);
     }
 }
 
+// Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states; the `beams` rows of query
+// blockIdx.x share the keys.  grid (Q, heads).
+__global__ void __launch_bounds__(512) cross_attn_kernel(int64_t Q, int d, int heads, int beams, int S,
+                                                         const float* __restrict__ q, const float* __restrict__ ckv,
+                                                         const int32_t* __restrict__ src_mask, float* __restrict__ out,
+                                                         float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    const int64_t qi = blockIdx.x;
+    const int h = blockIdx.y;
+    GroupAddr g{q + qi * beams * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
+    grouped_attention(g, beams, S, h * kHeadDim, qi * beams * d, d, out, out_hi, out_lo);
+}
+
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).
-// qkv [Q*S][3d].
-struct EncKV {
-    const float* base; const int32_t* mask; int d, col0;
-    __device__ __forceinline__ bool valid(int s) const { return mask[s] != 0; }
-    __device__ __forceinline__ const float* k(int s) const { return base + (int64_t)s * 3 * d + d + col0; }
-    __device__ __forceinline__ const float* v(int s) const { return base + (int64_t)s * 3 * d + 2 * d + col0; }
-};
-__global__ void __launch_bounds__(512, 2) enc_self_attn_kernel(int64_t tokens, int d, int heads, int S,
+// qkv [Q*S][3d].  grid (Q, heads).
+__global__ void __launch_bounds__(512) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,
                                                             const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ src_mask,
                                                             float* __restrict__ out, float* __restrict__ out_hi,
                                                             float* __restrict__ out_lo) {
-    __shared__ __align__(16) float q_s[16][kHeadDim];
-    const int64_t t = blockIdx.x;
-    const int64_t qi = t / S;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int h = warp; h < heads; h += blockDim.x >> 5) {
-        EncKV kv{qkv + qi * S * 3 * d, src_mask + qi * S, d, h * kHeadDim};
-        const float2 o = warp_attend(qkv + t * 3 * d + h * kHeadDim, S, kv, q_s[warp]);
-        store_attn(o, t * d + h * kHeadDim + lane * 2, out, out_hi, out_lo);
-    }
+    const int64_t qi = blockIdx.x;
+    const int h = blockIdx.y;
+    const float* base = qkv + qi * S * 3 * d;
+    GroupAddr g{base, 3 * d, base + d, base + 2 * d, 3 * d, src_mask + qi * S};
+    grouped_attention(g, S, S, h * kHeadDim, qi * S * d, d, out, out_hi, out_lo);
 }
 
 }  // namespace sealb200

@@ -302,7 +302,7 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     const int heads = m->cfg.heads;
     for (auto& L : m->enc) {
         gemm(cx, Tk, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        enc_self_attn_kernel<<<(unsigned)Tk, 32 * std::min(heads, 16), 0, cx.s>>>(Tk, d, heads, (int)D.S, qkv.x, m32, attn.x, attn.hi, attn.lo);
+        enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, attn.hi, attn.lo);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, Tk, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, Tk, d, x.x, tmp.x, L.ln_attn, x);
@@ -346,7 +346,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
-        cross_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, D.B, (int)D.S, cq.x,
+        cross_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
                                                                             attn.x, attn.hi, attn.lo);
         CUDA_CHECK(cudaGetLastError()); m->launches++;

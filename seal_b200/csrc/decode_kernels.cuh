@@ -149,7 +149,7 @@ __device__ void sel_merge(SelShared& S, int K) {
 }
 
 template <int DUMMY = 0>
-__global__ void __launch_bounds__(kSelThreads, 1) select_step_kernel(FmView fm, StepCfg c, StepState st) {
+__global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, StepCfg c, StepState st) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SelShared& S = *reinterpret_cast<SelShared*>(smem_raw);
     const int B = c.num_beams, K = c.K, V = c.V;
@@ -162,27 +162,29 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_step_kernel(FmView fm, 
     for (int b = 0; b < B; ++b) {
         const int64_t r = r0 + b;
         const float* lp = st.logits + r * c.ld;
-        // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251) --------------------
-        float mx = -INFINITY;
+        // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251), ONE streaming pass:
+        // per-thread running (max, sum exp(x - max)), merged across the block.
+        float mx = -INFINITY, se = 0.f;
         for (int v = tid * 4; v < V; v += kSelThreads * 4) {
+            float x0, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
             if (v + 3 < V) {
                 const float4 x = *reinterpret_cast<const float4*>(lp + v);
-                mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+                x0 = x.x; x1 = x.y; x2 = x.z; x3 = x.w;
             } else {
-                for (int u = v; u < V; ++u) mx = fmaxf(mx, lp[u]);
+                x0 = lp[v];
+                if (v + 1 < V) x1 = lp[v + 1];
+                if (v + 2 < V) x2 = lp[v + 2];
             }
+            const float m4 = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+            if (m4 > mx) { se *= expf(mx - m4); mx = m4; }          // mx = -inf: se is 0, expf(-inf) = 0
+            if (mx > -INFINITY) se += expf(x0 - mx) + expf(x1 - mx) + expf(x2 - mx) + expf(x3 - mx);
         }
-        mx = block_reduce_max(mx, S.red);
-        float se = 0.f;
-        for (int v = tid * 4; v < V; v += kSelThreads * 4) {
-            if (v + 3 < V) {
-                const float4 x = *reinterpret_cast<const float4*>(lp + v);
-                se += expf(x.x - mx) + expf(x.y - mx) + expf(x.z - mx) + expf(x.w - mx);
-            } else {
-                for (int u = v; u < V; ++u) se += expf(lp[u] - mx);
-            }
+        {
+            const float bm = block_reduce_max(mx, S.red);
+            const float scaled = (mx > -INFINITY) ? se * expf(mx - bm) : 0.f;
+            se = block_reduce_sum(scaled, S.red);
+            mx = bm;
         }
-        se = block_reduce_sum(se, S.red);
         const float logsum = logf(se);
         // ---- which tokens does the index allow on this row (seal/beam_search.py:87-135) ----------
         const int32_t* trow = st.tokens_in + r * c.T;

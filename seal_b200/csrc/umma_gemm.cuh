@@ -106,10 +106,10 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(int64_t n4, const float
 // into its fp32 TMEM accumulator with truncation, so a long K loop (K/8 x 3 sequential adds) drifts
 // by ~N_acc * 2^-24 relative, in one direction — 7e-6 at K = 1024, enough to push summed beam
 // scores past the 1e-4 parity bound.  Therefore the K loop is cut into chunks of UKC k-blocks
-// (K_c = 128): each chunk accumulates in one of two TMEM buffers (48 adds), and the epilogue warps
+// (K_c = 64): each chunk accumulates in one of two TMEM buffers (24 adds), and the epilogue warps
 // drain finished chunks into fp32 REGISTER accumulators with round-to-nearest adds while the next
 // chunk's MMAs run into the other buffer.
-constexpr int UKC = 4;                                       // k-blocks per TMEM chunk
+constexpr int UKC = 2;                                       // k-blocks per TMEM chunk (K_c = 64: 24 adds per chunk)
 constexpr int UEPI_WARPS = 16;                               // 4 lane quarters x 4 column groups of 64
 constexpr int UTHREADS2 = (4 + UEPI_WARPS) * 32;             // 640
 
