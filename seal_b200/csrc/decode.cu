@@ -182,9 +182,22 @@ void split_into(cudaStream_t s, const float* x, float* hi, float* lo, uint64_t n
 struct Act { float* x = nullptr; float* hi = nullptr; float* lo = nullptr; };
 
 void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& whi,
-                 const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu) {
+                 const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu, bool persistent) {
     using SMm = UmmaSmem<kUmmaBN>;
     dim3 grid((N + kUmmaBN - 1) / kUmmaBN, (unsigned)((M + UM - 1) / UM));
+    if (persistent) {
+        const int tiles = (int)(grid.x * grid.y);
+        const int ctas = std::min(tiles, sm_count());
+        if (gelu) {
+            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+        } else {
+            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     if (gelu) {
         CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
         umma_gemm_tf32x3_kernel<kUmmaBN, true><<<grid, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
@@ -200,7 +213,7 @@ void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi
 void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
     if (M == 0) return;
     sealbart* m = cx.m;
-    if (m->cfg.gemm_mode == 1 && K % UK == 0 && lda == K && l.w_hi) {
+    if (m->cfg.gemm_mode >= 1 && K % UK == 0 && lda == K && l.w_hi) {
         const float* ahi = A.hi; const float* alo = A.lo;
         if (!ahi) {
             m->a_hi.ensure((size_t)M * K * 4); m->a_lo.ensure((size_t)M * K * 4);
@@ -210,7 +223,7 @@ void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const
         CUtensorMap mah, mal;
         make_map(&mah, ahi, M, K, K, UM); make_map(&mal, alo, M, K, K, UM);
         if (!l.maps_ready) { make_map(&l.map_hi, l.w_hi, N, K, K, kUmmaBN); make_map(&l.map_lo, l.w_lo, N, K, K, kUmmaBN); l.maps_ready = true; }
-        umma_launch(cx.s, M, N, K, mah, mal, l.map_hi, l.map_lo, l.b, C, ldc, gelu);
+        umma_launch(cx.s, M, N, K, mah, mal, l.map_hi, l.map_lo, l.b, C, ldc, gelu, m->cfg.gemm_mode == 2);
         m->launches++;
         return;
     }
@@ -271,7 +284,7 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_scores.ensure(2 * D.R * 4); m->st_tokens.ensure(2 * D.R * D.T * 4);
     m->st_lo.ensure(2 * D.R * 8); m->st_hi.ensure(2 * D.R * 8); m->st_pw.ensure(2 * D.R * 8);
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
-    if (m->cfg.gemm_mode == 1) {
+    if (m->cfg.gemm_mode >= 1) {
         m->ex_hi.ensure(Tk * D.d * 4); m->ex_lo.ensure(Tk * D.d * 4);
         m->eattn_hi.ensure(Tk * D.d * 4); m->eattn_lo.ensure(Tk * D.d * 4);
         m->effn_hi.ensure(Tk * D.f * 4); m->effn_lo.ensure(Tk * D.f * 4);
@@ -289,7 +302,7 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     int32_t* tok = m->enc_tok.as<int32_t>(); int32_t* pos = tok + Tk; int32_t* m32 = m->enc_mask.as<int32_t>();
     prep_enc_kernel<<<(unsigned)((Tk + 255) / 256), 256, 0, cx.s>>>(Tk, (int)D.S, ids_d, mask_d, tok, m32, pos);
     CUDA_CHECK(cudaGetLastError()); m->launches++;
-    const bool sp = m->cfg.gemm_mode == 1;
+    const bool sp = m->cfg.gemm_mode >= 1;
     const Act x{m->ex.as<float>(), sp ? m->ex_hi.as<float>() : nullptr, sp ? m->ex_lo.as<float>() : nullptr};
     const Act qkv{m->eqkv.as<float>()};
     const Act attn{sp ? nullptr : m->eattn.as<float>(), sp ? m->eattn_hi.as<float>() : nullptr, sp ? m->eattn_lo.as<float>() : nullptr};
@@ -322,7 +335,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     sealbart* m = cx.m;
     const int d = D.d; const int64_t R = D.R; const int64_t Tk = D.Q * D.S;
     const int pos = cur_len - 1;
-    const bool sp = m->cfg.gemm_mode == 1;
+    const bool sp = m->cfg.gemm_mode >= 1;
     const Act x{m->dx.as<float>(), sp ? m->dx_hi.as<float>() : nullptr, sp ? m->dx_lo.as<float>() : nullptr};
     const Act qkv{m->dqkv.as<float>()};
     const Act attn{sp ? nullptr : m->dattn.as<float>(), sp ? m->dattn_hi.as<float>() : nullptr, sp ? m->dattn_lo.as<float>() : nullptr};
@@ -446,7 +459,7 @@ int sealbart_finalize(sealbart_t* m) {
             if (!m->loaded.count(kv.first)) throw ApiError(SEALFM_EINVAL, "state_dict tensor missing: " + kv.first);
         if (!m->lm_head_given) m->lm_head = m->shared;          // tied (seal/utils.py:48-49)
         m->head.w = m->lm_head; m->head.b = m->final_bias; m->head.out = m->cfg.vocab_size; m->head.in = m->cfg.d_model;
-        if (m->cfg.gemm_mode == 1) {
+        if (m->cfg.gemm_mode >= 1) {
             CUDA_CHECK(cudaSetDevice(m->device));
             for (void* p : m->split_allocs) cudaFree(p);
             m->split_allocs.clear();
@@ -672,7 +685,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         CUDA_CHECK(cudaMemcpy(dW.p, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
         if (bias) CUDA_CHECK(cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
         Lin l; l.w = dW.as<float>(); l.b = bias ? dB.as<float>() : nullptr; l.out = N; l.in = K;
-        if (mode == 1) {
+        if (mode >= 1) {
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
             split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);
