@@ -188,12 +188,13 @@ void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi
     if (persistent) {
         const int tiles = (int)(grid.x * grid.y);
         const int ctas = std::min(tiles, sm_count());
+        const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;     // stream the larger operand once
         if (gelu) {
             CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
         } else {
             CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
         }
         CUDA_CHECK(cudaGetLastError());
         return;

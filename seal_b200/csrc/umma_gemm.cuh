@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(UTHREADS2, 1)
 umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                         int M, int N, int K, const float* __restrict__ bias, float* __restrict__ C,
-                        float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc) {
+                        float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc, int n_fastest) {
     static_assert(BN == 256, "epilogue mapping assumes a 256-column tile (2 TMEM buffers = 512 columns)");
     using SM = UmmaSmem<BN>;
     extern __shared__ uint8_t smem_raw[];
@@ -271,8 +271,10 @@ umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, c
     const uint32_t tfull0 = bars + 16 * USTAGES, tempty0 = tfull0 + 16;   // 2 TMEM buffers
     const uint32_t slot = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // persistent: CTA b walks tiles b, b + gridDim.x, ...; m fastest so that concurrently running
-    // CTAs share the same W tile (L2 hit) and the activations stay L2-resident across n tiles
+    // persistent: CTA b walks tiles b, b + gridDim.x, ...  Tile order is chosen by the host so that
+    // the LARGER operand is streamed from HBM once: n fastest when the activations dominate (the
+    // concurrently running CTAs then share A tiles and all of W stays in L2), m fastest when the
+    // weights dominate (lm_head).
     const int m_tiles = (M + UM - 1) / UM, n_tiles = (N + BN - 1) / BN;
     const int total_tiles = m_tiles * n_tiles;
     const int num_k = K / UK;
@@ -296,7 +298,7 @@ umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, c
         if (lane == 0) {
             uint32_t it = 0;                                   // k-blocks issued so far (all tiles)
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+            const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % USTAGES;
                 const uint32_t ph = (it / USTAGES) & 1;
@@ -349,7 +351,7 @@ umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, c
         const int cg = (warp - 4) >> 2;                        // column group: 64 columns
         uint32_t ch = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile % m_tiles, n_tile = tile / m_tiles;
+        const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
         float acc[64];
 #pragma unroll
         for (int j = 0; j < 64; ++j) acc[j] = 0.f;
