@@ -3,6 +3,7 @@
 // seal/beam_search.py:231-238,481-483).  Post-LN encoder/decoder layers, learned positions with
 // offset 2, layernorm_embedding, exact-erf GELU, tied lm_head + final_logits_bias.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -32,12 +33,57 @@ __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
     split1(v.x, h.x, l.x); split1(v.y, h.y, l.y); split1(v.z, h.z, l.z); split1(v.w, h.w, l.w);
 }
 
+// Where a producer writes the operand split its consumer GEMM wants: kind 0 = none, 1 = TF32 (two
+// fp32 arrays), 2 = FP16 (two half arrays; saturates at +-65504 and raises *overflow).
+struct SplitOut { void* a = nullptr; void* b = nullptr; int kind = 0; int* overflow = nullptr; };
+
+__device__ __forceinline__ void half_split1(float x, __half& h1, __half& h2, int& ov) {
+    if (fabsf(x) > 65504.f) { ov = 1; x = copysignf(65504.f, x); }
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(x - __half2float(h1));
+}
+__device__ __forceinline__ void store_split4(const SplitOut& so, int64_t idx, const float4& o) {
+    if (so.kind == 1) {
+        float4 h, l;
+        split4(o, h, l);
+        *reinterpret_cast<float4*>(static_cast<float*>(so.a) + idx) = h;
+        *reinterpret_cast<float4*>(static_cast<float*>(so.b) + idx) = l;
+    } else if (so.kind == 2) {
+        __half h1[4], h2[4];
+        int ov = 0;
+        half_split1(o.x, h1[0], h2[0], ov); half_split1(o.y, h1[1], h2[1], ov);
+        half_split1(o.z, h1[2], h2[2], ov); half_split1(o.w, h1[3], h2[3], ov);
+        if (ov) atomicExch(so.overflow, 1);
+        *reinterpret_cast<uint2*>(static_cast<__half*>(so.a) + idx) = make_uint2(
+            (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16),
+            (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16));
+        *reinterpret_cast<uint2*>(static_cast<__half*>(so.b) + idx) = make_uint2(
+            (uint32_t)__half_as_ushort(h2[0]) | ((uint32_t)__half_as_ushort(h2[1]) << 16),
+            (uint32_t)__half_as_ushort(h2[2]) | ((uint32_t)__half_as_ushort(h2[3]) << 16));
+    }
+}
+__device__ __forceinline__ void store_split2(const SplitOut& so, int64_t idx, const float2& o) {
+    if (so.kind == 1) {
+        float2 h, l;
+        split1(o.x, h.x, l.x); split1(o.y, h.y, l.y);
+        *reinterpret_cast<float2*>(static_cast<float*>(so.a) + idx) = h;
+        *reinterpret_cast<float2*>(static_cast<float*>(so.b) + idx) = l;
+    } else if (so.kind == 2) {
+        __half a0, a1, b0, b1;
+        int ov = 0;
+        half_split1(o.x, a0, b0, ov); half_split1(o.y, a1, b1, ov);
+        if (ov) atomicExch(so.overflow, 1);
+        *reinterpret_cast<uint32_t*>(static_cast<__half*>(so.a) + idx) = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
+        *reinterpret_cast<uint32_t*>(static_cast<__half*>(so.b) + idx) = (uint32_t)__half_as_ushort(b0) | ((uint32_t)__half_as_ushort(b1) << 16);
+    }
+}
+
 // LayerNorm of one row held as `per` float4 per lane (d = 128*per), torch semantics:
 // biased variance, eps inside the sqrt, fp32.
 template <int MAXV>
 __device__ __forceinline__ void warp_layernorm(float4 (&v)[MAXV], int nv, int d, const float* __restrict__ gamma,
                                                const float* __restrict__ beta, float eps, float* __restrict__ out,
-                                               float* __restrict__ out_hi, float* __restrict__ out_lo, int lane) {
+                                               const SplitOut& so, int64_t row_off, int lane) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) if (i < nv) s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -59,13 +105,8 @@ __device__ __forceinline__ void warp_layernorm(float4 (&v)[MAXV], int nv, int d,
         o.y = (v[i].y - mean) * rstd * g.y + b.y;
         o.z = (v[i].z - mean) * rstd * g.z + b.z;
         o.w = (v[i].w - mean) * rstd * g.w + b.w;
-        if (out) *reinterpret_cast<float4*>(out + col) = o;
-        if (out_hi) {
-            float4 h, l;
-            split4(o, h, l);
-            *reinterpret_cast<float4*>(out_hi + col) = h;
-            *reinterpret_cast<float4*>(out_lo + col) = l;
-        }
+        if (out) *reinterpret_cast<float4*>(out + row_off + col) = o;
+        store_split4(so, row_off + col, o);
     }
 }
 
@@ -79,8 +120,7 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
                                                        const float* __restrict__ embed, float scale,
                                                        const float* __restrict__ pos_table,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       float* __restrict__ out, float* __restrict__ out_hi,
-                                                       float* __restrict__ out_lo) {
+                                                       float* __restrict__ out, SplitOut so) {
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -96,15 +136,14 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
         const float4 b = *reinterpret_cast<const float4*>(pe + col);
         v[i] = make_float4(a.x * scale + b.x, a.y * scale + b.y, a.z * scale + b.z, a.w * scale + b.w);
     }
-    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out ? out + r * d : nullptr,
-                              out_hi ? out_hi + r * d : nullptr, out_lo ? out_lo + r * d : nullptr, lane);
+    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out, so, r * d, lane);
 }
 
 // out[r] = LN(a[r] + b[r])     (residual + sub-layer output, post-LN)
 __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                      const float* __restrict__ b, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ out,
-                                                     float* __restrict__ out_hi, float* __restrict__ out_lo) {
+                                                     SplitOut so) {
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -117,8 +156,7 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
         const float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
         v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
     }
-    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out ? out + r * d : nullptr,
-                              out_hi ? out_hi + r * d : nullptr, out_lo ? out_lo + r * d : nullptr, lane);
+    warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out, so, r * d, lane);
 }
 
 // ---- fp32 SIMT GEMM:  C[M,N] = A[M,K] * W[N,K]^T + bias[N]  (optionally GELU) ---------------------
@@ -257,15 +295,9 @@ __device__ __forceinline__ float2 warp_attend(const float* __restrict__ q_head, 
     return make_float2(ax / l, ay / l);
 }
 
-__device__ __forceinline__ void store_attn(float2 o, int64_t idx, float* __restrict__ out, float* __restrict__ out_hi,
-                                           float* __restrict__ out_lo) {
+__device__ __forceinline__ void store_attn(float2 o, int64_t idx, float* __restrict__ out, const SplitOut& so) {
     if (out) *reinterpret_cast<float2*>(out + idx) = o;
-    if (out_hi) {
-        float2 h, l;
-        split1(o.x, h.x, l.x); split1(o.y, h.y, l.y);
-        *reinterpret_cast<float2*>(out_hi + idx) = h;
-        *reinterpret_cast<float2*>(out_lo + idx) = l;
-    }
+    store_split2(so, idx, o);
 }
 
 // Decoder self-attention for one new token per row with beam-ancestry indirection instead of a
@@ -287,8 +319,7 @@ struct SelfKV {
 __global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
                                                             const float* __restrict__ qkv, float* kc, float* vc,
                                                             const int32_t* __restrict__ anc,
-                                                            float* __restrict__ out, float* __restrict__ out_hi,
-                                                            float* __restrict__ out_lo) {
+                                                            float* __restrict__ out, SplitOut so) {
     __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -301,7 +332,7 @@ __global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d,
         SelfKV kv{kc, vc, anc + r * T, qkv + r * 3 * d + d + h * kHeadDim, qkv + r * 3 * d + 2 * d + h * kHeadDim,
                   R, d, h * kHeadDim, cur_pos};
         const float2 o = warp_attend(qkv + r * 3 * d + h * kHeadDim, cur_pos + 1, kv, q_s[warp]);
-        store_attn(o, r * d + col, out, out_hi, out_lo);
+        store_attn(o, r * d + col, out, so);
     }
 }
 
@@ -317,8 +348,7 @@ struct GroupAddr {
 };
 
 __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, int n_keys, int head_off, int64_t out_base,
-                                                  int64_t out_stride, float* __restrict__ out, float* __restrict__ out_hi,
-                                                  float* __restrict__ out_lo) {
+                                                  int64_t out_stride, float* __restrict__ out, const SplitOut& so) {
     __shared__ float Kt[kHeadDim][33];
     __shared__ __align__(16) float Vs[32][kHeadDim];
     __shared__ __align__(16) float q_s[16][kHeadDim];
@@ -373,7 +403,7 @@ __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, 
                 }
             }
         }
-        if (has_row) store_attn(make_float2(ax / l, ay / l), out_base + r * out_stride + head_off + 2 * lane, out, out_hi, out_lo);
+        if (has_row) store_attn(make_float2(ax / l, ay / l), out_base + r * out_stride + head_off + 2 * lane, out, so);
     }
 }
 
@@ -382,11 +412,11 @@ __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, 
 __global__ void __launch_bounds__(512) cross_attn_kernel(int64_t Q, int d, int heads, int beams, int S,
                                                          const float* __restrict__ q, const float* __restrict__ ckv,
                                                          const int32_t* __restrict__ src_mask, float* __restrict__ out,
-                                                         float* __restrict__ out_hi, float* __restrict__ out_lo) {
+                                                         SplitOut so) {
     const int64_t qi = blockIdx.x;
     const int h = blockIdx.y;
     GroupAddr g{q + qi * beams * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
-    grouped_attention(g, beams, S, h * kHeadDim, qi * beams * d, d, out, out_hi, out_lo);
+    grouped_attention(g, beams, S, h * kHeadDim, qi * beams * d, d, out, so);
 }
 
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).
@@ -394,13 +424,12 @@ __global__ void __launch_bounds__(512) cross_attn_kernel(int64_t Q, int d, int h
 __global__ void __launch_bounds__(512) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,
                                                             const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ src_mask,
-                                                            float* __restrict__ out, float* __restrict__ out_hi,
-                                                            float* __restrict__ out_lo) {
+                                                            float* __restrict__ out, SplitOut so) {
     const int64_t qi = blockIdx.x;
     const int h = blockIdx.y;
     const float* base = qkv + qi * S * 3 * d;
     GroupAddr g{base, 3 * d, base + d, base + 2 * d, 3 * d, src_mask + qi * S};
-    grouped_attention(g, S, S, h * kHeadDim, qi * S * d, d, out, out_hi, out_lo);
+    grouped_attention(g, S, S, h * kHeadDim, qi * S * d, d, out, so);
 }
 
 }  // namespace sealb200

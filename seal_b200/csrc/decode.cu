@@ -23,7 +23,9 @@ namespace {
 
 struct Lin {
     float* w = nullptr; float* b = nullptr; int out = 0, in = 0;
-    float* w_hi = nullptr; float* w_lo = nullptr;          // TF32 split copies (gemm_mode 1)
+    float* w_hi = nullptr; float* w_lo = nullptr;          // TF32 split copies (gemm_mode 1, 2)
+    __half* w_h1 = nullptr; __half* w_h2 = nullptr;        // FP16 split copies of W * 2^s (gemm_mode 3)
+    float w_unscale = 1.f;                                 // 2^-s
     CUtensorMap map_hi{}, map_lo{}; bool maps_ready = false;
 };
 struct LNp { float* g = nullptr; float* b = nullptr; };
@@ -156,13 +158,13 @@ EncodeTiledFn encode_tiled() {
     }
     return fn;
 }
-// row-major [rows][K] fp32, box = 32 (K) x box_rows, 128B swizzle, zero fill out of bounds
-void make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
+// row-major [rows][K] fp32 (or fp16), box = 128 bytes of K x box_rows, 128B swizzle, zero fill out of bounds
+void make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, bool half = false) {
     cuuint64_t dims[2] = {K, rows};
-    cuuint64_t strides[1] = {ld * sizeof(float)};
-    cuuint32_t box[2] = {UK, box_rows};
+    cuuint64_t strides[1] = {ld * (half ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(half ? UK16 : UK), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode_tiled()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+    CUresult r = encode_tiled()(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw ApiError(SEALFM_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -179,7 +181,17 @@ void split_into(cudaStream_t s, const float* x, float* hi, float* lo, uint64_t n
 }
 
 // An activation tensor as the GEMMs see it: plain fp32 and/or its TF32 split (hi, lo).
-struct Act { float* x = nullptr; float* hi = nullptr; float* lo = nullptr; };
+struct Act {
+    float* x = nullptr; float* hi = nullptr; float* lo = nullptr;   // fp32 / TF32 split
+    __half* h1 = nullptr; __half* h2 = nullptr;                     // FP16 split
+};
+
+SplitOut split_of(const Act& a, int* overflow) {
+    SplitOut so;
+    if (a.hi) { so.a = a.hi; so.b = a.lo; so.kind = 1; }
+    else if (a.h1) { so.a = a.h1; so.b = a.h2; so.kind = 2; so.overflow = overflow; }
+    return so;
+}
 
 void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& whi,
                  const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu, bool persistent) {
@@ -214,7 +226,35 @@ void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi
 void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
     if (M == 0) return;
     sealbart* m = cx.m;
-    if (m->cfg.gemm_mode >= 1 && K % UK == 0 && lda == K && l.w_hi) {
+    if (m->cfg.gemm_mode == 3 && K % UK16 == 0 && lda == K && l.w_h1) {
+        // 3xFP16 on tcgen05 (persistent); operands pre-split into halves by the producers
+        const __half* a1 = A.h1; const __half* a2 = A.h2;
+        if (!a1) {
+            m->a_hi.ensure((size_t)M * K * 2); m->a_lo.ensure((size_t)M * K * 2);
+            const int blocks = (int)std::min<int64_t>(((int64_t)M * K + 255) / 256, (int64_t)sm_count() * 8);
+            split_half_kernel<<<blocks, 256, 0, cx.s>>>((int64_t)M * K, A.x, 1.0f, m->a_hi.as<__half>(), m->a_lo.as<__half>(), m->err.as<int>() + 1);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            a1 = m->a_hi.as<__half>(); a2 = m->a_lo.as<__half>();
+        }
+        CUtensorMap ma1, ma2;
+        make_map(&ma1, a1, M, K, K, UM, true); make_map(&ma2, a2, M, K, K, UM, true);
+        if (!l.maps_ready) { make_map(&l.map_hi, l.w_h1, N, K, K, kUmmaBN, true); make_map(&l.map_lo, l.w_h2, N, K, K, kUmmaBN, true); l.maps_ready = true; }
+        using SMm = UmmaSmem<kUmmaBN>;
+        const int tiles = (int)(((N + kUmmaBN - 1) / kUmmaBN) * ((M + UM - 1) / UM));
+        const int ctas = std::min(tiles, sm_count());
+        const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;
+        int* ovf = m->err.as<int>() + 1;
+        if (gelu) {
+            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+            umma_gemm_f16x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+        } else {
+            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+            umma_gemm_f16x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+        }
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        return;
+    }
+    if (m->cfg.gemm_mode >= 1 && m->cfg.gemm_mode <= 2 && K % UK == 0 && lda == K && l.w_hi) {
         const float* ahi = A.hi; const float* alo = A.lo;
         if (!ahi) {
             m->a_hi.ensure((size_t)M * K * 4); m->a_lo.ensure((size_t)M * K * 4);
@@ -238,7 +278,7 @@ void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const
 }
 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
-    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out.x, out.hi, out.lo);
+    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out.x, split_of(out, cx.m->err.as<int>() + 1));
     CUDA_CHECK(cudaGetLastError());
     cx.m->launches++;
 }
@@ -293,7 +333,7 @@ void ensure_workspace(sealbart* m, const Dims& D) {
         m->dattn_hi.ensure(D.R * D.d * 4); m->dattn_lo.ensure(D.R * D.d * 4);
         m->dffn_hi.ensure(D.R * D.f * 4); m->dffn_lo.ensure(D.R * D.f * 4);
     }
-    m->err.ensure(4);
+    m->err.ensure(8);
 }
 
 void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t* mask_d) {
@@ -303,20 +343,28 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     int32_t* tok = m->enc_tok.as<int32_t>(); int32_t* pos = tok + Tk; int32_t* m32 = m->enc_mask.as<int32_t>();
     prep_enc_kernel<<<(unsigned)((Tk + 255) / 256), 256, 0, cx.s>>>(Tk, (int)D.S, ids_d, mask_d, tok, m32, pos);
     CUDA_CHECK(cudaGetLastError()); m->launches++;
-    const bool sp = m->cfg.gemm_mode >= 1;
-    const Act x{m->ex.as<float>(), sp ? m->ex_hi.as<float>() : nullptr, sp ? m->ex_lo.as<float>() : nullptr};
+    const int gm = m->cfg.gemm_mode;
+    auto mk = [&](float* plain, Buf& bh, Buf& bl, bool keep_plain) {
+        Act a;
+        if (gm == 0 || keep_plain) a.x = plain;
+        if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
+        if (gm == 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
+        return a;
+    };
+    int* ovf = m->err.as<int>() + 1;
+    const Act x = mk(m->ex.as<float>(), m->ex_hi, m->ex_lo, true);
     const Act qkv{m->eqkv.as<float>()};
-    const Act attn{sp ? nullptr : m->eattn.as<float>(), sp ? m->eattn_hi.as<float>() : nullptr, sp ? m->eattn_lo.as<float>() : nullptr};
+    const Act attn = mk(m->eattn.as<float>(), m->eattn_hi, m->eattn_lo, false);
     const Act tmp{m->etmp.as<float>()};
-    const Act ffn{sp ? nullptr : m->effn.as<float>(), sp ? m->effn_hi.as<float>() : nullptr, sp ? m->effn_lo.as<float>() : nullptr};
+    const Act ffn = mk(m->effn.as<float>(), m->effn_hi, m->effn_lo, false);
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
     embed_ln_kernel<<<(unsigned)((Tk + 3) / 4), 128, 0, cx.s>>>(Tk, d, tok, 1, pos, 0, m->shared, scale, m->enc_pos,
-                                                                m->enc_ln_emb.g, m->enc_ln_emb.b, x.x, x.hi, x.lo);
+                                                                m->enc_ln_emb.g, m->enc_ln_emb.b, x.x, split_of(x, ovf));
     CUDA_CHECK(cudaGetLastError()); m->launches++;
     const int heads = m->cfg.heads;
     for (auto& L : m->enc) {
         gemm(cx, Tk, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, attn.hi, attn.lo);
+        enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, Tk, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, Tk, d, x.x, tmp.x, L.ln_attn, x);
@@ -336,16 +384,24 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     sealbart* m = cx.m;
     const int d = D.d; const int64_t R = D.R; const int64_t Tk = D.Q * D.S;
     const int pos = cur_len - 1;
-    const bool sp = m->cfg.gemm_mode >= 1;
-    const Act x{m->dx.as<float>(), sp ? m->dx_hi.as<float>() : nullptr, sp ? m->dx_lo.as<float>() : nullptr};
+    const int gm = m->cfg.gemm_mode;
+    auto mk = [&](float* plain, Buf& bh, Buf& bl, bool keep_plain) {
+        Act a;
+        if (gm == 0 || keep_plain) a.x = plain;
+        if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
+        if (gm == 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
+        return a;
+    };
+    int* ovf = m->err.as<int>() + 1;
+    const Act x = mk(m->dx.as<float>(), m->dx_hi, m->dx_lo, true);
     const Act qkv{m->dqkv.as<float>()};
-    const Act attn{sp ? nullptr : m->dattn.as<float>(), sp ? m->dattn_hi.as<float>() : nullptr, sp ? m->dattn_lo.as<float>() : nullptr};
+    const Act attn = mk(m->dattn.as<float>(), m->dattn_hi, m->dattn_lo, false);
     const Act tmp{m->dtmp.as<float>()};
     const Act cq{m->dcq.as<float>()};
-    const Act ffn{sp ? nullptr : m->dffn.as<float>(), sp ? m->dffn_hi.as<float>() : nullptr, sp ? m->dffn_lo.as<float>() : nullptr};
+    const Act ffn = mk(m->dffn.as<float>(), m->dffn_hi, m->dffn_lo, false);
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
     embed_ln_kernel<<<(unsigned)((R + 3) / 4), 128, 0, cx.s>>>(R, d, tokens + pos, D.T, nullptr, pos, m->shared, scale,
-                                                               m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x.x, x.hi, x.lo);
+                                                               m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x.x, split_of(x, ovf));
     CUDA_CHECK(cudaGetLastError()); m->launches++;
     const int heads = m->cfg.heads;
     const int32_t* m32 = m->enc_mask.as<int32_t>();
@@ -355,14 +411,14 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         float* vc = m->vc.as<float>() + (size_t)l * D.T * R * d;
         gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         dec_self_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
-                                                                               attn.x, attn.hi, attn.lo);
+                                                                               attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
         cross_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
-                                                                            attn.x, attn.hi, attn.lo);
+                                                                            attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
@@ -472,6 +528,33 @@ int sealbart_finalize(sealbart_t* m) {
                 l.maps_ready = false;
                 m->weight_bytes += 2 * n * 4;
             };
+            unsigned int* d_max = nullptr;
+            if (m->cfg.gemm_mode == 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(8); CUDA_CHECK(cudaMemset(m->err.p, 0, 8)); }
+            auto split_lin_half = [&](Lin& l) {
+                const uint64_t n = (uint64_t)l.out * l.in;
+                CUDA_CHECK(cudaMemset(d_max, 0, 4));
+                absmax_kernel<<<sm_count() * 4, 256>>>((int64_t)n, l.w, d_max);
+                unsigned int bits = 0; CUDA_CHECK(cudaMemcpy(&bits, d_max, 4, cudaMemcpyDeviceToHost));
+                float mx; std::memcpy(&mx, &bits, 4);
+                int sexp = 0;
+                if (mx > 0.f) { int e; std::frexp(mx, &e); sexp = 14 - e; }      // max|W| * 2^s in [2^13, 2^14)
+                l.w_unscale = std::ldexp(1.0f, -sexp);
+                CUDA_CHECK(cudaMalloc(&l.w_h1, n * 2)); m->split_allocs.push_back(l.w_h1);
+                CUDA_CHECK(cudaMalloc(&l.w_h2, n * 2)); m->split_allocs.push_back(l.w_h2);
+                split_half_kernel<<<sm_count() * 8, 256>>>((int64_t)n, l.w, std::ldexp(1.0f, sexp), l.w_h1, l.w_h2, m->err.as<int>() + 1);
+                CUDA_CHECK(cudaGetLastError());
+                l.maps_ready = false;
+                m->weight_bytes += 2 * n * 2;
+            };
+            if (m->cfg.gemm_mode == 3) {
+                for (auto& L : m->enc) { split_lin_half(L.qkv); split_lin_half(L.o); split_lin_half(L.fc1); split_lin_half(L.fc2); }
+                for (auto& L : m->dec) { split_lin_half(L.qkv); split_lin_half(L.o); split_lin_half(L.cq); split_lin_half(L.ckv); split_lin_half(L.co); split_lin_half(L.fc1); split_lin_half(L.fc2); }
+                split_lin_half(m->head);
+                CUDA_CHECK(cudaDeviceSynchronize());
+                cudaFree(d_max);
+                m->finalized = true;
+                return;
+            }
             for (auto& L : m->enc) { split_lin(L.qkv); split_lin(L.o); split_lin(L.fc1); split_lin(L.fc2); }
             for (auto& L : m->dec) { split_lin(L.qkv); split_lin(L.o); split_lin(L.cq); split_lin(L.ckv); split_lin(L.co); split_lin(L.fc1); split_lin(L.fc2); }
             split_lin(m->head);
@@ -537,6 +620,7 @@ int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d,
                                                                         lo0, hi0, sc[0], tk[0], lo[0], hi[0], pw[0], an[0]);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         CUDA_CHECK(cudaMemsetAsync(err_d, 0, 4, cx.s));
+        CUDA_CHECK(cudaMemsetAsync(m->err.as<int>() + 1, 0, 4, cx.s));
 
         StepCfg c{};
         c.num_beams = B; c.K = K; c.V = D.V; c.ld = D.ld;
@@ -623,7 +707,7 @@ int sealdec_generate(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_host
         CUDA_CHECK(cudaMemcpyAsync(d_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
         if (occ_host) CUDA_CHECK(cudaMemcpyAsync(d_occ.p, occ_host, (size_t)W * 4, cudaMemcpyHostToDevice, s));
         m->hy_score.ensure(Q * H * 4); m->hy_len.ensure(Q * H * 4); m->hy_tok.ensure(Q * H * T * 4);
-        m->hy_valid.ensure(Q * H); m->hy_lo.ensure(Q * H * 8); m->hy_hi.ensure(Q * H * 8); m->err.ensure(4);
+        m->hy_valid.ensure(Q * H); m->hy_lo.ensure(Q * H * 8); m->hy_hi.ensure(Q * H * 8); m->err.ensure(8);
         int rc = sealdec_generate_d(m, fm, occ_host ? d_occ.as<uint32_t>() : nullptr, p, d_ids.as<int64_t>(), d_mask.as<int64_t>(),
                                     Q, S, s, m->hy_score.as<float>(), m->hy_len.as<int32_t>(), m->hy_tok.as<int32_t>(),
                                     m->hy_valid.as<uint8_t>(), o_lo ? m->hy_lo.as<uint64_t>() : nullptr,
@@ -635,9 +719,11 @@ int sealdec_generate(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_host
         CUDA_CHECK(cudaMemcpyAsync(o_valid, m->hy_valid.p, Q * H, cudaMemcpyDeviceToHost, s));
         if (o_lo) CUDA_CHECK(cudaMemcpyAsync(o_lo, m->hy_lo.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
         if (o_hi) CUDA_CHECK(cudaMemcpyAsync(o_hi, m->hy_hi.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
-        int32_t err = 0;
-        CUDA_CHECK(cudaMemcpyAsync(&err, m->err.p, 4, cudaMemcpyDeviceToHost, s));
+        int32_t errs[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(errs, m->err.p, 8, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+        const int32_t err = errs[0];
+        if (errs[1]) throw ApiError(SEALFM_EINVAL, "fp16 range exceeded in the 3xFP16 GEMM path (|x| > 65504); use gemm_mode 2 (3xTF32)");
         if (err) throw ApiError(SEALFM_EINVAL, "beam: fewer than num_beams non-EOS candidates (seal/beam_search.py:687-690)");
     });
 }
@@ -679,17 +765,28 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         sealbart fake; fake.cfg.gemm_mode = mode;
         CUDA_CHECK(cudaGetDevice(&fake.device));
         Buf dA, dW, dB, dC, whi, wlo;
-        struct Rel { std::vector<Buf*> v; sealbart* f; ~Rel() { for (auto b : v) b->release(); f->a_hi.release(); f->a_lo.release(); } } rel{{&dA, &dW, &dB, &dC, &whi, &wlo}, &fake};
+        struct Rel { std::vector<Buf*> v; sealbart* f; ~Rel() { for (auto b : v) b->release(); f->a_hi.release(); f->a_lo.release(); f->err.release(); } } rel{{&dA, &dW, &dB, &dC, &whi, &wlo}, &fake};
         const int ldc = (N + 3) / 4 * 4;
         dA.ensure((size_t)M * K * 4); dW.ensure((size_t)N * K * 4); dB.ensure((size_t)N * 4); dC.ensure((size_t)M * ldc * 4);
         CUDA_CHECK(cudaMemcpy(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));
         CUDA_CHECK(cudaMemcpy(dW.p, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
         if (bias) CUDA_CHECK(cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
         Lin l; l.w = dW.as<float>(); l.b = bias ? dB.as<float>() : nullptr; l.out = N; l.in = K;
-        if (mode >= 1) {
+        fake.err.ensure(8); CUDA_CHECK(cudaMemset(fake.err.p, 0, 8));
+        if (mode == 1 || mode == 2) {
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
             split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);
+        } else if (mode == 3) {
+            whi.ensure((size_t)N * K * 2); wlo.ensure((size_t)N * K * 2);
+            l.w_h1 = whi.as<__half>(); l.w_h2 = wlo.as<__half>();
+            float mx = 0.f;
+            for (int64_t i = 0; i < (int64_t)N * K; ++i) mx = std::max(mx, std::fabs(W[i]));
+            int sexp = 0;
+            if (mx > 0.f) { int e; std::frexp(mx, &e); sexp = 14 - e; }
+            l.w_unscale = std::ldexp(1.0f, -sexp);
+            split_half_kernel<<<sm_count() * 8, 256>>>((int64_t)N * K, l.w, std::ldexp(1.0f, sexp), l.w_h1, l.w_h2, fake.err.as<int>() + 1);
+            CUDA_CHECK(cudaGetLastError());
         }
         Ctx cx{&fake, nullptr};
         gemm(cx, M, N, K, Act{dA.as<float>()}, K, l, Act{dC.as<float>()}, ldc, gelu != 0);

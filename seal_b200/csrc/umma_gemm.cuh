@@ -10,6 +10,7 @@
 // allocator, 4..7 = epilogue.  One CTA per 128 x BN output tile.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 
@@ -395,6 +396,214 @@ umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, c
                     for (int u = 0; u < 4; ++u) if (n + u < N) {
                         if (C) C[roff + n + u] = v[u];
                         if (C_hi) { C_hi[roff + n + u] = vh[u]; C_lo[roff + n + u] = vl[u]; }
+                    }
+                }
+            }
+        }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- 3xFP16 variant (gemm_mode 3) -------------------------------------------------------------------
+// Same persistent skeleton, operands split into two IEEE half values instead of two TF32 values:
+//   x = h1 + h2 (+ <= 2^-22 |x|),  h1 = rn_half(x), h2 = rn_half(x - h1);   A*W ~= A2*W1 + A1*W2 + A1*W1.
+// fp16 products are exact in the fp32 accumulator, so the accuracy class is the same as 3xTF32, but an
+// element costs 4 bytes instead of 8 (the TF32 kernel is bound by L2->shared-memory operand traffic,
+// profiles/r01_ncu_umma_fc1_raw.csv: tensor pipe 65 % active) and kind::f16 runs at twice the TF32
+// rate.  Range: activations are used unscaled (|x| must stay below 65504; the producers saturate and
+// raise a sticky flag otherwise, and the absolute floor of a subnormal h2, 3e-8, is far below the
+// 1e-5 logit budget); each weight matrix is pre-multiplied by a power of two 2^s so that
+// max|W| ~ 2^14 and the epilogue multiplies the accumulator by 2^-s (exact).
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int UK16 = 64;            // k-block: 64 halves = 128 B = one swizzle row
+constexpr float kHalfMax = 65504.f;
+
+__device__ __forceinline__ void split_half(float x, __half& h1, __half& h2, int* overflow) {
+    if (fabsf(x) > kHalfMax) { if (overflow) *overflow = 1; x = copysignf(kHalfMax, x); }
+    h1 = __float2half_rn(x);
+    h2 = __float2half_rn(x - __half2float(h1));
+}
+
+// x * scale -> (h1, h2) halves; used for weights (once) and for activations whose producer did not split
+__global__ void __launch_bounds__(256) split_half_kernel(int64_t n, const float* __restrict__ x, float scale,
+                                                         __half* __restrict__ h1, __half* __restrict__ h2,
+                                                         int* __restrict__ overflow) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        __half a, b;
+        int ov = 0;
+        split_half(x[i] * scale, a, b, &ov);
+        if (ov) atomicExch(overflow, 1);
+        h1[i] = a; h2[i] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256) absmax_kernel(int64_t n, const float* __restrict__ x, unsigned int* __restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(x[i]);
+        if (v == v && v != INFINITY) m = fmaxf(m, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));       // non-negative floats order like uints
+}
+
+template <int BN, bool GELU>
+__global__ void __launch_bounds__(UTHREADS2, 1)
+umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                        const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                        int M, int N, int K, const float* __restrict__ bias, float w_unscale, float* __restrict__ C,
+                        __half* __restrict__ C_h1, __half* __restrict__ C_h2, int ldc, int n_fastest,
+                        int* __restrict__ overflow) {
+    static_assert(BN == 256, "epilogue mapping assumes a 256-column tile (2 TMEM buffers = 512 columns)");
+    using SM = UmmaSmem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024 B alignment
+    const uint32_t bars = base + USTAGES * SM::kStageBytes;
+    const uint32_t full0 = bars, empty0 = bars + 8 * USTAGES;             // smem stage barriers
+    const uint32_t tfull0 = bars + 16 * USTAGES, tempty0 = tfull0 + 16;   // 2 TMEM buffers
+    const uint32_t slot = tempty0 + 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // persistent: CTA b walks tiles b, b + gridDim.x, ...  Tile order is chosen by the host so that
+    // the LARGER operand is streamed from HBM once: n fastest when the activations dominate (the
+    // concurrently running CTAs then share A tiles and all of W stays in L2), m fastest when the
+    // weights dominate (lm_head).
+    const int m_tiles = (M + UM - 1) / UM, n_tiles = (N + BN - 1) / BN;
+    const int total_tiles = m_tiles * n_tiles;
+    const int num_k = K / UK16;
+    const int num_chunks = (num_k + UKC - 1) / UKC;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < USTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, UEPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;                                   // k-blocks issued so far (all tiles)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
+            for (int kb = 0; kb < num_k; ++kb, ++it) {
+                const int s = it % USTAGES;
+                const uint32_t ph = (it / USTAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t st = base + s * SM::kStageBytes;
+                mbar_expect_tx(full0 + 8 * s, SM::kStageBytes);
+                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UK16, m_tile * UM);
+                tma_load_2d(st + SM::kABytes, &tmA_lo, full0 + 8 * s, kb * UK16, m_tile * UM);
+                tma_load_2d(st + 2 * SM::kABytes, &tmW_hi, full0 + 8 * s, kb * UK16, n_tile * BN);
+                tma_load_2d(st + 2 * SM::kABytes + SM::kWBytes, &tmW_lo, full0 + 8 * s, kb * UK16, n_tile * BN);
+            }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=F32 (1<<4), A=B=F16 (format 0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
+            uint32_t it = 0, ch = 0;                           // k-blocks / chunks consumed so far (all tiles)
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int kb = 0;
+            for (int c = 0; c < num_chunks; ++c, ++ch) {
+                const int buf = ch & 1;
+                mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);    // epilogue has drained this buffer's previous use
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
+                const int kend = (kb + UKC < num_k) ? kb + UKC : num_k;
+                for (int k0 = kb; kb < kend; ++kb, ++it) {
+                    const int s = it % USTAGES;
+                    const uint32_t ph = (it / USTAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * SM::kStageBytes;
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + SM::kABytes);
+                    const uint64_t w_hi = umma_desc_sw128(st + 2 * SM::kABytes), w_lo = umma_desc_sw128(st + 2 * SM::kABytes + SM::kWBytes);
+#pragma unroll
+                    for (int k = 0; k < UK16 / 16; ++k) {      // UMMA_K = 16 halves = 32 B -> +2 in the >>4 address field
+                        umma_f16(tacc, a_lo + 2 * k, w_hi + 2 * k, idesc, (kb != k0) || (k != 0));
+                        umma_f16(tacc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
+                        umma_f16(tacc, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
+                    }
+                    umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
+                }
+                umma_commit(tfull0 + 8 * buf);                 // this chunk's partial sums are complete
+            }
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;                                // TMEM lane quarter this warp may touch (warp % 4)
+        const int cg = (warp - 4) >> 2;                        // column group: 64 columns
+        uint32_t ch = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+        for (int c = 0; c < num_chunks; ++c, ++ch) {
+            const int buf = ch & 1;
+            mbar_wait(tfull0 + 8 * buf, (ch >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cg * 64 + h * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += __uint_as_float(r[j]);      // round-to-nearest promotion
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
+        }
+        const int row = m_tile * UM + q * 32 + lane;
+        const int nb = n_tile * BN + cg * 64;
+        if (row < M && nb < N) {
+            const int64_t roff = (int64_t)row * ldc;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+                const int n = nb + j;
+                float v[4];
+                __half h1[4], h2[4];
+                int ov = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float x = acc[j + u] * w_unscale + ((bias && n + u < N) ? bias[n + u] : 0.f);
+                    v[u] = GELU ? gelu_erf_u(x) : x;
+                    if (C_h1) split_half(v[u], h1[u], h2[u], &ov);
+                }
+                if (ov) atomicExch(overflow, 1);
+                if (n + 3 < N) {
+                    if (C) *reinterpret_cast<float4*>(C + roff + n) = make_float4(v[0], v[1], v[2], v[3]);
+                    if (C_h1) {
+                        *reinterpret_cast<uint2*>(C_h1 + roff + n) = make_uint2(
+                            (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16),
+                            (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16));
+                        *reinterpret_cast<uint2*>(C_h2 + roff + n) = make_uint2(
+                            (uint32_t)__half_as_ushort(h2[0]) | ((uint32_t)__half_as_ushort(h2[1]) << 16),
+                            (uint32_t)__half_as_ushort(h2[2]) | ((uint32_t)__half_as_ushort(h2[3]) << 16));
+                    }
+                } else {
+                    for (int u = 0; u < 4; ++u) if (n + u < N) {
+                        if (C) C[roff + n + u] = v[u];
+                        if (C_h1) { C_h1[roff + n + u] = h1[u]; C_h2[roff + n + u] = h2[u]; }
                     }
                 }
             }
