@@ -198,7 +198,8 @@ def run_ours(args):
     flops_head = 2.0 * R * d * V * (MAX_LEN - 1)
     gemm_s = (phases["decoder_layers"] + phases["lm_head"]) * 1e-6
     n_gemm = (7 * Ld + 1) * (MAX_LEN - 1)
-    roof = {"bound": "tensor", "kernel": "sgemm_tn_kernel" if args.gemm_mode == 0 else "tf32x3_umma_gemm",
+    roof = {"bound": "tensor", "kernel": {0: "sgemm_tn_kernel", 1: "umma_gemm_tf32x3_kernel", 2: "umma_gemm_tf32x3_persistent_kernel",
+                                          3: "umma_gemm_f16x3_persistent_kernel"}[args.gemm_mode],
             "achieved": (flops_layers + flops_head) / gemm_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
             "frac": (flops_layers + flops_head) / gemm_s / 1e12 / tf_sus, "traffic": None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",
@@ -298,7 +299,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--queries", type=int, default=1000)
     ap.add_argument("--ref-queries", type=int, default=2, help="queries per step of the CPU reference sample")
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("SEALB200_GEMM", "0")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("SEALB200_GEMM", "3")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
