@@ -56,7 +56,7 @@ typedef struct {
     int32_t ffn_dim;           /* 4096                                         */
     int32_t max_positions;     /* 1024 (+2 learned offset)                     */
     int32_t scale_embedding;   /* 0 for bart-large                             */
-    int32_t gemm_mode;         /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16 */
+    int32_t gemm_mode;         /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = same with 64B rows / 4-stage pipeline */
 } sealbart_config_t;
 
 int  sealbart_create(const sealbart_config_t* cfg, int device, sealbart_t** out);
@@ -130,7 +130,7 @@ int sealdec_debug_step_logits(sealbart_t* model, const int64_t* input_ids, const
                               int64_t Q, int64_t S, int32_t num_beams, const int64_t* decoder_input_ids,
                               int64_t t, float* out_logits);
 /* Stand-alone GEMM C[M,N] = A[M,K] W[N,K]^T + bias (+GELU) through the model's GEMM kernels
- * (mode 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16), host pointers; if iters > 0 also reports the average
+ * (mode 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = 3xFP16 4-stage), host pointers; if iters > 0 also reports the average
  * device time per call (CUDA events, includes the activation split in mode 1). */
 int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A, const float* W,
                        const float* bias, float* C, int32_t gelu, int32_t iters, double* avg_us);

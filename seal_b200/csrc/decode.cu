@@ -159,13 +159,15 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 // row-major [rows][K] fp32 (or fp16), box = 128 bytes of K x box_rows, 128B swizzle, zero fill out of bounds
-void make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, bool half = false) {
+void make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows, bool half = false,
+              int row_bytes = 128) {
     cuuint64_t dims[2] = {K, rows};
     cuuint64_t strides[1] = {ld * (half ? 2 : 4)};
-    cuuint32_t box[2] = {(cuuint32_t)(half ? UK16 : UK), box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)(row_bytes / (half ? 2 : 4)), box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_tiled()(map, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw ApiError(SEALFM_ECUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
@@ -226,7 +228,8 @@ void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi
 void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
     if (M == 0) return;
     sealbart* m = cx.m;
-    if (m->cfg.gemm_mode == 3 && K % UK16 == 0 && lda == K && l.w_h1) {
+    if (m->cfg.gemm_mode >= 3 && K % UK16 == 0 && lda == K && l.w_h1) {
+        const int rowb = m->cfg.gemm_mode == 4 ? 64 : 128;
         // 3xFP16 on tcgen05 (persistent); operands pre-split into halves by the producers
         const __half* a1 = A.h1; const __half* a2 = A.h2;
         if (!a1) {
@@ -237,20 +240,19 @@ void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const
             a1 = m->a_hi.as<__half>(); a2 = m->a_lo.as<__half>();
         }
         CUtensorMap ma1, ma2;
-        make_map(&ma1, a1, M, K, K, UM, true); make_map(&ma2, a2, M, K, K, UM, true);
-        if (!l.maps_ready) { make_map(&l.map_hi, l.w_h1, N, K, K, kUmmaBN, true); make_map(&l.map_lo, l.w_h2, N, K, K, kUmmaBN, true); l.maps_ready = true; }
+        make_map(&ma1, a1, M, K, K, UM, true, rowb); make_map(&ma2, a2, M, K, K, UM, true, rowb);
+        if (!l.maps_ready) { make_map(&l.map_hi, l.w_h1, N, K, K, kUmmaBN, true, rowb); make_map(&l.map_lo, l.w_h2, N, K, K, kUmmaBN, true, rowb); l.maps_ready = true; }
         using SMm = UmmaSmem<kUmmaBN>;
         const int tiles = (int)(((N + kUmmaBN - 1) / kUmmaBN) * ((M + UM - 1) / UM));
         const int ctas = std::min(tiles, sm_count());
         const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;
         int* ovf = m->err.as<int>() + 1;
-        if (gelu) {
-            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_f16x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
-        } else {
-            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_f16x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
-        }
+        auto launch = [&](auto kern) {
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+            kern<<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+        };
+        if (rowb == 128) { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>); }
+        else { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 64>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>); }
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         return;
     }
@@ -348,7 +350,7 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
         Act a;
         if (gm == 0 || keep_plain) a.x = plain;
         if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
-        if (gm == 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
+        if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
     int* ovf = m->err.as<int>() + 1;
@@ -389,7 +391,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         Act a;
         if (gm == 0 || keep_plain) a.x = plain;
         if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
-        if (gm == 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
+        if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
     int* ovf = m->err.as<int>() + 1;
@@ -529,7 +531,7 @@ int sealbart_finalize(sealbart_t* m) {
                 m->weight_bytes += 2 * n * 4;
             };
             unsigned int* d_max = nullptr;
-            if (m->cfg.gemm_mode == 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(8); CUDA_CHECK(cudaMemset(m->err.p, 0, 8)); }
+            if (m->cfg.gemm_mode >= 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(8); CUDA_CHECK(cudaMemset(m->err.p, 0, 8)); }
             auto split_lin_half = [&](Lin& l) {
                 const uint64_t n = (uint64_t)l.out * l.in;
                 CUDA_CHECK(cudaMemset(d_max, 0, 4));
@@ -546,7 +548,7 @@ int sealbart_finalize(sealbart_t* m) {
                 l.maps_ready = false;
                 m->weight_bytes += 2 * n * 2;
             };
-            if (m->cfg.gemm_mode == 3) {
+            if (m->cfg.gemm_mode >= 3) {
                 for (auto& L : m->enc) { split_lin_half(L.qkv); split_lin_half(L.o); split_lin_half(L.fc1); split_lin_half(L.fc2); }
                 for (auto& L : m->dec) { split_lin_half(L.qkv); split_lin_half(L.o); split_lin_half(L.cq); split_lin_half(L.ckv); split_lin_half(L.co); split_lin_half(L.fc1); split_lin_half(L.fc2); }
                 split_lin_half(m->head);
@@ -777,7 +779,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
             split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);
-        } else if (mode == 3) {
+        } else if (mode >= 3) {
             whi.ensure((size_t)N * K * 2); wlo.ensure((size_t)N * K * 2);
             l.w_h1 = whi.as<__half>(); l.w_h2 = wlo.as<__half>();
             float mx = 0.f;

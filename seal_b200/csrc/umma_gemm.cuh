@@ -459,7 +459,17 @@ __global__ void __launch_bounds__(256) absmax_kernel(int64_t n, const float* __r
     if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));       // non-negative floats order like uints
 }
 
-template <int BN, bool GELU>
+// K-major shared-memory matrix descriptor for 128-byte (SWIZZLE_128B) or 64-byte (SWIZZLE_64B) rows:
+// 8-row groups are ROWB*8 bytes apart (SBO); layout code 2 / 4 (cute/arch/mma_sm100_desc.hpp).
+template <int ROWB>
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    static_assert(ROWB == 128 || ROWB == 64, "row bytes");
+    constexpr uint64_t sbo = (ROWB * 8) >> 4;
+    constexpr uint64_t layout = ROWB == 128 ? 2 : 4;
+    return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+template <int BN, bool GELU, int ROWB>
 __global__ void __launch_bounds__(UTHREADS2, 1)
 umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
@@ -467,12 +477,19 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                         __half* __restrict__ C_h1, __half* __restrict__ C_h2, int ldc, int n_fastest,
                         int* __restrict__ overflow) {
     static_assert(BN == 256, "epilogue mapping assumes a 256-column tile (2 TMEM buffers = 512 columns)");
-    using SM = UmmaSmem<BN>;
+    // ROWB = bytes of K per shared-memory row: 128 -> SWIZZLE_128B, 64 K-halves per k-block, 2 stages of
+    // 96 KB; 64 -> SWIZZLE_64B, 32 K-halves per k-block, 4 stages of 48 KB (three loads in flight
+    // instead of one: the 2-stage kernel leaves the tensor pipe idle ~35 % of the time waiting for TMA,
+    // profiles/r01_ncu_umma_fc1_raw.csv).
+    constexpr int NST = (ROWB == 128) ? 2 : 4;
+    constexpr int KE = ROWB / 2;                                           // K halves per k-block
+    constexpr int kAB = UM * ROWB, kWB = BN * ROWB, kStage = 2 * kAB + 2 * kWB;
+    constexpr int kChunkBlocks = (ROWB == 128) ? UKC : 2 * UKC;            // same K per TMEM chunk (128)
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024 B alignment
-    const uint32_t bars = base + USTAGES * SM::kStageBytes;
-    const uint32_t full0 = bars, empty0 = bars + 8 * USTAGES;             // smem stage barriers
-    const uint32_t tfull0 = bars + 16 * USTAGES, tempty0 = tfull0 + 16;   // 2 TMEM buffers
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms want 1024 B alignment
+    const uint32_t bars = base + NST * kStage;
+    const uint32_t full0 = bars, empty0 = bars + 8 * NST;                 // smem stage barriers
+    const uint32_t tfull0 = bars + 16 * NST, tempty0 = tfull0 + 16;       // 2 TMEM buffers
     const uint32_t slot = tempty0 + 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // persistent: CTA b walks tiles b, b + gridDim.x, ...  Tile order is chosen by the host so that
@@ -481,11 +498,11 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     // weights dominate (lm_head).
     const int m_tiles = (M + UM - 1) / UM, n_tiles = (N + BN - 1) / BN;
     const int total_tiles = m_tiles * n_tiles;
-    const int num_k = K / UK16;
-    const int num_chunks = (num_k + UKC - 1) / UKC;
+    const int num_k = K / KE;
+    const int num_chunks = (num_k + kChunkBlocks - 1) / kChunkBlocks;
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < USTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, UEPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
@@ -504,15 +521,15 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
-                const int s = it % USTAGES;
-                const uint32_t ph = (it / USTAGES) & 1;
+                const int s = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
-                const uint32_t st = base + s * SM::kStageBytes;
-                mbar_expect_tx(full0 + 8 * s, SM::kStageBytes);
-                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UK16, m_tile * UM);
-                tma_load_2d(st + SM::kABytes, &tmA_lo, full0 + 8 * s, kb * UK16, m_tile * UM);
-                tma_load_2d(st + 2 * SM::kABytes, &tmW_hi, full0 + 8 * s, kb * UK16, n_tile * BN);
-                tma_load_2d(st + 2 * SM::kABytes + SM::kWBytes, &tmW_lo, full0 + 8 * s, kb * UK16, n_tile * BN);
+                const uint32_t st = base + s * kStage;
+                mbar_expect_tx(full0 + 8 * s, kStage);
+                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * KE, m_tile * UM);
+                tma_load_2d(st + kAB, &tmA_lo, full0 + 8 * s, kb * KE, m_tile * UM);
+                tma_load_2d(st + 2 * kAB, &tmW_hi, full0 + 8 * s, kb * KE, n_tile * BN);
+                tma_load_2d(st + 2 * kAB + kWB, &tmW_lo, full0 + 8 * s, kb * KE, n_tile * BN);
             }
             }
         }
@@ -528,17 +545,17 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                 mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);    // epilogue has drained this buffer's previous use
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                const int kend = (kb + UKC < num_k) ? kb + UKC : num_k;
+                const int kend = (kb + kChunkBlocks < num_k) ? kb + kChunkBlocks : num_k;
                 for (int k0 = kb; kb < kend; ++kb, ++it) {
-                    const int s = it % USTAGES;
-                    const uint32_t ph = (it / USTAGES) & 1;
+                    const int s = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
-                    const uint32_t st = base + s * SM::kStageBytes;
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + SM::kABytes);
-                    const uint64_t w_hi = umma_desc_sw128(st + 2 * SM::kABytes), w_lo = umma_desc_sw128(st + 2 * SM::kABytes + SM::kWBytes);
+                    const uint32_t st = base + s * kStage;
+                    const uint64_t a_hi = umma_desc<ROWB>(st), a_lo = umma_desc<ROWB>(st + kAB);
+                    const uint64_t w_hi = umma_desc<ROWB>(st + 2 * kAB), w_lo = umma_desc<ROWB>(st + 2 * kAB + kWB);
 #pragma unroll
-                    for (int k = 0; k < UK16 / 16; ++k) {      // UMMA_K = 16 halves = 32 B -> +2 in the >>4 address field
+                    for (int k = 0; k < KE / 16; ++k) {        // UMMA_K = 16 halves = 32 B -> +2 in the >>4 address field
                         umma_f16(tacc, a_lo + 2 * k, w_hi + 2 * k, idesc, (kb != k0) || (k != 0));
                         umma_f16(tacc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
                         umma_f16(tacc, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);

@@ -34,7 +34,7 @@ SHAPES = [(5, 128, 128, False), (77, 384, 128, False), (300, 1024, 1024, False),
           (513, 1024, 4096, False), (200, 1003, 1024, False), (6, 50265, 1024, False)]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("M,N,K,gelu", SHAPES)
 def test_gemm_matches_float64(mode, M, N, K, gelu):
     rng = np.random.default_rng(M * 7 + N)
@@ -56,6 +56,6 @@ def test_gemm_throughput_report():
     for (M, N, K) in [(15000, 4096, 1024), (15000, 1024, 4096), (15000, 3072, 1024), (3000, 50265, 1024)]:
         A = rng.standard_normal((M, K)).astype(np.float32); W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
         b = np.zeros(N, dtype=np.float32)
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             _, us = run_gemm(mode, A, W, b, False, iters=5)
             print(f"GEMM {M}x{N}x{K} mode {mode}: {us:.1f} us, {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (fp32-equivalent)")
