@@ -199,7 +199,7 @@ def run_ours(args):
     gemm_s = (phases["decoder_layers"] + phases["lm_head"]) * 1e-6
     n_gemm = (7 * Ld + 1) * (MAX_LEN - 1)
     roof = {"bound": "tensor", "kernel": {0: "sgemm_tn_kernel", 1: "umma_gemm_tf32x3_kernel", 2: "umma_gemm_tf32x3_persistent_kernel",
-                                          3: "umma_gemm_f16x3_persistent_kernel"}[args.gemm_mode],
+                                          3: "umma_gemm_f16x3_persistent_kernel", 4: "umma_gemm_f16x3_persistent_kernel<ROWB=64>"}[args.gemm_mode],
             "achieved": (flops_layers + flops_head) / gemm_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
             "frac": (flops_layers + flops_head) / gemm_s / 1e12 / tf_sus, "traffic": None,
             "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",

@@ -303,36 +303,84 @@ __device__ __forceinline__ void store_attn(float2 o, int64_t idx, float* __restr
 // Decoder self-attention for one new token per row with beam-ancestry indirection instead of a
 // cache reorder (the reference index_selects 24 cache tensors per step, seal/beam_search.py:331-332).
 // qkv: [R][3d] (q | k | v) of the current position; kc/vc: [T][R][d] per layer; anc: [R][T] source row
-// of every earlier position.  Writes this position's k,v into the cache first.
-struct SelfKV {
-    const float* kc; const float* vc; const int32_t* anc; const float* cur_k; const float* cur_v;
-    int64_t R; int d, col0, cur_pos;
-    __device__ __forceinline__ bool valid(int) const { return true; }
-    // the current position's k/v are read from this step's qkv, never back from the cache just written
-    __device__ __forceinline__ const float* k(int s) const {
-        return s == cur_pos ? cur_k : kc + ((int64_t)s * R + anc[s]) * d + col0;
-    }
-    __device__ __forceinline__ const float* v(int s) const {
-        return s == cur_pos ? cur_v : vc + ((int64_t)s * R + anc[s]) * d + col0;
-    }
-};
+// of every earlier position.  One warp per (row, head), split into 4 groups of 8 lanes: a group owns
+// one key at a time and each of its lanes 8 of the 64 head dims, so four K (then V) rows stream
+// concurrently with two 16-byte loads per lane — the key count here is tiny (<= max_length), so
+// lane-per-key would leave most lanes idle.  The current position's k/v are taken from qkv (and
+// written to the cache for the later steps).
 __global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
-                                                            const float* __restrict__ qkv, float* kc, float* vc,
-                                                            const int32_t* __restrict__ anc,
-                                                            float* __restrict__ out, SplitOut so) {
-    __shared__ __align__(16) float q_s[16][kHeadDim];
+                                                               const float* __restrict__ qkv, float* kc, float* vc,
+                                                               const int32_t* __restrict__ anc,
+                                                               float* __restrict__ out, SplitOut so) {
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, i8 = (lane & 7) * 8;
+    const int n_keys = cur_pos + 1;                            // <= 32
+    const int32_t* arow = anc + r * T;
     for (int h = warp; h < heads; h += blockDim.x >> 5) {
-        const int col = h * kHeadDim + lane * 2;
-        const float2 k = *reinterpret_cast<const float2*>(qkv + r * 3 * d + d + col);
-        const float2 v = *reinterpret_cast<const float2*>(qkv + r * 3 * d + 2 * d + col);
-        *reinterpret_cast<float2*>(kc + ((int64_t)cur_pos * R + r) * d + col) = k;
-        *reinterpret_cast<float2*>(vc + ((int64_t)cur_pos * R + r) * d + col) = v;
-        SelfKV kv{kc, vc, anc + r * T, qkv + r * 3 * d + d + h * kHeadDim, qkv + r * 3 * d + 2 * d + h * kHeadDim,
-                  R, d, h * kHeadDim, cur_pos};
-        const float2 o = warp_attend(qkv + r * 3 * d + h * kHeadDim, cur_pos + 1, kv, q_s[warp]);
-        store_attn(o, r * d + col, out, so);
+        const int col = h * kHeadDim + i8;
+        const float* qp = qkv + r * 3 * d + col;
+        const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
+        const float* kcur = qp + d; const float* vcur = qp + 2 * d;
+        if (g == 0) {                                          // persist this position's k, v
+            float* kd = kc + ((int64_t)cur_pos * R + r) * d + col; float* vd = vc + ((int64_t)cur_pos * R + r) * d + col;
+            *reinterpret_cast<float4*>(kd) = *reinterpret_cast<const float4*>(kcur);
+            *reinterpret_cast<float4*>(kd + 4) = *reinterpret_cast<const float4*>(kcur + 4);
+            *reinterpret_cast<float4*>(vd) = *reinterpret_cast<const float4*>(vcur);
+            *reinterpret_cast<float4*>(vd + 4) = *reinterpret_cast<const float4*>(vcur + 4);
+        }
+        float sc[8];
+        float mloc = -INFINITY;
+#pragma unroll
+        for (int rd = 0; rd < 8; ++rd) {
+            const int s = rd * 4 + g;
+            sc[rd] = -INFINITY;
+            if (rd * 4 < n_keys) {                             // warp-uniform
+                float part = 0.f;
+                if (s < n_keys) {
+                    const float* kp = (s == cur_pos) ? kcur : kc + ((int64_t)s * R + arow[s]) * d + col;
+                    const float4 k0 = *reinterpret_cast<const float4*>(kp), k1 = *reinterpret_cast<const float4*>(kp + 4);
+                    part = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+                }
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);
+                part += __shfl_xor_sync(0xffffffffu, part, 4);
+                if (s < n_keys) { sc[rd] = part * 0.125f; mloc = fmaxf(mloc, sc[rd]); }
+            }
+        }
+        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 8));
+        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 16));
+        float lsum = 0.f;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+        for (int rd = 0; rd < 8; ++rd) {
+            const int s = rd * 4 + g;
+            if (rd * 4 < n_keys && s < n_keys) {
+                const float p = expf(sc[rd] - mloc);
+                lsum += p;
+                const float* vp = (s == cur_pos) ? vcur : vc + ((int64_t)s * R + arow[s]) * d + col;
+                const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
+                a0.x = fmaf(p, v0.x, a0.x); a0.y = fmaf(p, v0.y, a0.y); a0.z = fmaf(p, v0.z, a0.z); a0.w = fmaf(p, v0.w, a0.w);
+                a1.x = fmaf(p, v1.x, a1.x); a1.y = fmaf(p, v1.y, a1.y); a1.z = fmaf(p, v1.z, a1.z); a1.w = fmaf(p, v1.w, a1.w);
+            }
+        }
+        // every lane of a group holds the same p's: the group sum counts each key once per lane -> use lane 0's view
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            a0.x += __shfl_xor_sync(0xffffffffu, a0.x, o); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, o);
+            a0.z += __shfl_xor_sync(0xffffffffu, a0.z, o); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, o);
+            a1.x += __shfl_xor_sync(0xffffffffu, a1.x, o); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, o);
+            a1.z += __shfl_xor_sync(0xffffffffu, a1.z, o); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, o);
+        }
+        if (g == 0) {
+            const float inv = 1.0f / lsum;
+            const float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+            const float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
+            const int64_t idx = r * d + col;
+            if (out) { *reinterpret_cast<float4*>(out + idx) = o0; *reinterpret_cast<float4*>(out + idx + 4) = o1; }
+            store_split4(so, idx, o0); store_split4(so, idx + 4, o1);
+        }
     }
 }
 

@@ -97,7 +97,7 @@ struct SelShared {
     uint8_t row_rule[kSelMaxBeams];       // 0 index set, 1 only eos, 2 only pad
     float red[kSelThreads / 32];
     float rv[kSelThreads / 32]; int ri[kSelThreads / 32]; int rslot[kSelThreads / 32];
-    int ccount, tcount;
+    int ccount, tcount, overflow;
     float thr; int thr_idx;
     int nbeam_src[kSelMaxBeams];          // candidate index feeding each new beam
     int n_noneos;
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
     const int64_t qi = blockIdx.x;
     const int64_t r0 = qi * B;
     const int tid = threadIdx.x;
-    if (tid == 0) { S.ccount = 0; S.tcount = 0; S.thr = -INFINITY; S.thr_idx = 0x7fffffff; S.n_noneos = 0; }
+    if (tid == 0) { S.ccount = 0; S.tcount = 0; S.overflow = 0; S.thr = -INFINITY; S.thr_idx = 0x7fffffff; S.n_noneos = 0; }
     __syncthreads();
 
     for (int b = 0; b < B; ++b) {
@@ -202,38 +202,66 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         }
         if (tid == 0) { S.row_max[b] = mx; S.row_logsum[b] = logsum; S.row_rule[b] = (uint8_t)rule; }
         const float bs = st.beam_scores_in[r];
-        // ---- stage candidates whose constrained score is finite and not below the running k-th best
-        for (int w0 = 0; w0 < c.mask_words; w0 += kSelThreads) {
-            const int w = w0 + tid;
-            uint32_t bits = 0;
-            if (w < c.mask_words) {
-                if (c.disable_fm_index) bits = 0xffffffffu;
-                else if (c.forced_bos_token_id >= 0 && c.cur_len == 1) bits = (c.forced_bos_token_id >> 5) == w ? 1u << (c.forced_bos_token_id & 31) : 0u;
-                else if (rule == 1) bits = (c.eos_token_id >> 5) == w ? 1u << (c.eos_token_id & 31) : 0u;
-                else if (rule == 2) bits = (c.pad_token_id >> 5) == w ? 1u << (c.pad_token_id & 31) : 0u;
-                else bits = mrow[w];
-                if (c.always_allow_eos && !c.disable_fm_index && !(c.forced_bos_token_id >= 0 && c.cur_len == 1) &&
-                    (c.eos_token_id >> 5) == w) bits |= 1u << (c.eos_token_id & 31);
-                if (w == c.mask_words - 1 && (V & 31)) bits &= (1u << (V & 31)) - 1;
+        // ---- stage candidates whose constrained score is finite and not below the running k-th best.
+        // Fast path: one barrier-free sweep over the row's mask words (rows allow a handful of tokens
+        // after the first step); if the staging buffer would overflow (first step: ~47 k allowed
+        // tokens) the row is redone in bounded sub-rounds with a merge between them.
+        auto row_bits = [&](int w) -> uint32_t {
+            uint32_t bits;
+            if (c.disable_fm_index) bits = 0xffffffffu;
+            else if (c.forced_bos_token_id >= 0 && c.cur_len == 1) bits = (c.forced_bos_token_id >> 5) == w ? 1u << (c.forced_bos_token_id & 31) : 0u;
+            else if (rule == 1) bits = (c.eos_token_id >> 5) == w ? 1u << (c.eos_token_id & 31) : 0u;
+            else if (rule == 2) bits = (c.pad_token_id >> 5) == w ? 1u << (c.pad_token_id & 31) : 0u;
+            else bits = mrow[w];
+            if (c.always_allow_eos && !c.disable_fm_index && !(c.forced_bos_token_id >= 0 && c.cur_len == 1) &&
+                (c.eos_token_id >> 5) == w) bits |= 1u << (c.eos_token_id & 31);
+            if (w == c.mask_words - 1 && (V & 31)) bits &= (1u << (V & 31)) - 1;
+            return bits;
+        };
+        auto consider = [&](int v, bool guarded) {
+            float p = (lp[v] - mx) - logsum;
+            p = apply_processors(c, v, p);
+            const float s = p + bs;
+            const int flat = b * V + v;
+            if (s > -INFINITY && (S.tcount < K || cand_better(s, flat, S.thr, S.thr_idx))) {
+                const int slot = atomicAdd(&S.ccount, 1);
+                if (!guarded || slot < kSelBuf) { S.cval[slot] = s; S.cidx[slot] = flat; }
+                else S.overflow = 1;
             }
-            for (int sub = 0; sub < 4; ++sub) {
-                uint32_t part = (bits >> (8 * sub)) & 0xffu;
-                while (part) {
-                    const int bit = __ffs(part) - 1; part &= part - 1;
-                    const int v = w * 32 + 8 * sub + bit;
-                    float p = (lp[v] - mx) - logsum;
-                    p = apply_processors(c, v, p);
-                    const float s = p + bs;
-                    const int flat = b * V + v;
-                    if (s > -INFINITY && (S.tcount < K || cand_better(s, flat, S.thr, S.thr_idx))) {
-                        const int slot = atomicAdd(&S.ccount, 1);
-                        S.cval[slot] = s; S.cidx[slot] = flat;
+        };
+        __syncthreads();
+        const int count_before = S.ccount;
+        for (int w = tid; w < c.mask_words; w += kSelThreads) {
+            uint32_t bits = row_bits(w);
+            while (bits) {
+                const int bit = __ffs(bits) - 1; bits &= bits - 1;
+                consider(w * 32 + bit, true);
+            }
+        }
+        __syncthreads();
+        const bool overflow = S.overflow != 0;                   // uniform: read between two barriers
+        const int staged_fast = S.ccount;
+        __syncthreads();
+        if (!overflow) {
+            if (staged_fast > kSelBuf / 2) sel_merge(S, K);      // keep room for the next rows
+        } else {
+            if (tid == 0) { S.ccount = count_before; S.overflow = 0; }
+            __syncthreads();
+            if (count_before > 0) sel_merge(S, K);
+            for (int w0 = 0; w0 < c.mask_words; w0 += kSelThreads) {
+                const int w = w0 + tid;
+                const uint32_t bits = w < c.mask_words ? row_bits(w) : 0u;
+                for (int sub = 0; sub < 4; ++sub) {
+                    uint32_t part = (bits >> (8 * sub)) & 0xffu;
+                    while (part) {
+                        const int bit = __ffs(part) - 1; part &= part - 1;
+                        consider(w * 32 + 8 * sub + bit, false);
                     }
+                    __syncthreads();
+                    const int staged = S.ccount;                 // read between two barriers:
+                    __syncthreads();                             // the branch below is uniform
+                    if (staged > kSelBuf - kSelThreads * 8) sel_merge(S, K);
                 }
-                __syncthreads();
-                const int staged = S.ccount;                                 // read between two barriers:
-                __syncthreads();                                             // the branch below is uniform
-                if (staged > kSelBuf - kSelThreads * 8) sel_merge(S, K);
             }
         }
     }

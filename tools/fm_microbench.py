@@ -91,6 +91,35 @@ def main():
             out["cpu_count"] = os.cpu_count()
     except Exception as ex:  # pragma: no cover
         out["ref_error"] = repr(ex)
+    # ---- beyond-L2 index: the metric's "rank-kernel HBM GB/s" needs the tree in DRAM, not in L2 ----
+    big = int(os.environ.get("FMB_BIG", "0"))
+    if big:
+        del fm
+        torch.cuda.empty_cache()
+        rng2 = np.random.default_rng(1)
+        p = 1.0 / (np.arange(50000) + 1.0); cdf = np.cumsum(p / p.sum())
+        t = time.time()
+        btext = (np.minimum(np.searchsorted(cdf, rng2.random(big)), 49999) + 14).astype(np.uint64)
+        out["big_corpus_s"] = time.time() - t
+        t = time.time(); bfm = FMIndex(); bfm.initialize(btext); out["big_build_s"] = time.time() - t
+        bfm.to_device(0)
+        bm = bfm.size()
+        from seal_b200._lib import lib
+        out["big_index_device_MB"] = lib.sealfm_device_bytes(bfm._h) / 1e6
+        res = {}
+        for N in (15000, 1 << 18, 1 << 22):
+            sym = torch.tensor(btext[rng2.integers(0, big, size=N)].astype(np.int64), device=dev)
+            lo = torch.randint(0, bm // 2, (N,), device=dev); hi = lo + torch.randint(1, bm // 2, (N,), device=dev)
+            t_lf = cuda_time(lambda: bfm.lf_step_tensors(sym, lo, hi), iters=10)
+            res[N] = {"us": t_lf * 1e6, "steps_per_s": N / t_lf, "alg_GBps": N * 48 * L / t_lf / 1e9,
+                      "sector_GBps": N * (64 + 16) * L / t_lf / 1e9}
+        out["big_lf"] = res
+        # expansion of narrow ranges (typical decode rows): width 1..64
+        R = 1 << 16
+        lo = torch.randint(0, bm - 100, (R,), device=dev); hi = lo + torch.randint(1, 64, (R,), device=dev)
+        mask = bfm.expand_mask_tensors(lo, hi, V)
+        t_ex = cuda_time(lambda: bfm.expand_mask_tensors(lo, hi, V, out=mask), iters=5)
+        out["big_expand_narrow"] = {"R": R, "us": t_ex * 1e6}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "fm_microbench.json"), "w") as f:
         json.dump(out, f, indent=1)
