@@ -23,6 +23,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "queries/sec at beam=15, 1k queries, 10M-token index; rank-kernel HBM GB/s"
 BEAM, MIN_LEN, MAX_LEN, LP = 15, 10, 10, 0.0          # SEALSearcher body defaults (retrieval.py:70-83)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the fc1-shaped GEMM (M=15000, N=4096, K=1024) from
+# `ncu --set full` (profiles/r01_ncu_*_raw.csv); algorithmic bytes of that launch: A 61 MB + W 17 MB + C 246 MB.
+TRAFFIC_PER_LAUNCH = {2: 438.3e6}
 
 
 def peaks():
@@ -192,22 +195,47 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, which = peaks()
-    # ---- roofline of the dominant kernel (the decoder/lm_head GEMM) ----------------------------------
-    R = Q * BEAM; d = cfg.d_model; V = cfg.vocab_size; Ld = cfg.decoder_layers
-    flops_layers = 2.0 * R * (12 * d * d + 2 * d * cfg.decoder_ffn_dim) * Ld * (MAX_LEN - 1)   # qkv,o,cq,co + fc1,fc2
-    flops_head = 2.0 * R * d * V * (MAX_LEN - 1)
-    gemm_s = (phases["decoder_layers"] + phases["lm_head"]) * 1e-6
-    n_gemm = (7 * Ld + 1) * (MAX_LEN - 1)
+    # ---- roofline of the dominant kernel (the decoder/encoder/lm_head GEMM), measured live: one extra
+    # pass with every GEMM launch bracketed by CUDA events on its stream --------------------------------
+    eng.profile_gemm(True)
+    step_device(); torch.cuda.synchronize()
+    prof = eng.profile_gemm(False)
+    gemm_s = prof["total_us"] * 1e-6
+    passes = {0: 1, 1: 3, 2: 3, 3: 3, 4: 3}[args.gemm_mode]
+    ach = prof["flops"] / gemm_s / 1e12
     roof = {"bound": "tensor", "kernel": {0: "sgemm_tn_kernel", 1: "umma_gemm_tf32x3_kernel", 2: "umma_gemm_tf32x3_persistent_kernel",
                                           3: "umma_gemm_f16x3_persistent_kernel", 4: "umma_gemm_f16x3_persistent_kernel<ROWB=64>"}[args.gemm_mode],
-            "achieved": (flops_layers + flops_head) / gemm_s / 1e12, "peak": tf_sus, "unit": "TFLOP/s",
-            "frac": (flops_layers + flops_head) / gemm_s / 1e12 / tf_sus, "traffic": None,
-            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which})",
-            "note": "algorithmic decoder+lm_head GEMM flops / CUDA-event time of the decoder-layer and lm_head "
-                    "phases (includes the small attention/LN kernels between GEMMs); avg per GEMM launch "
-                    f"{gemm_s / n_gemm * 1e6:.1f} us over {n_gemm} launches"}
-    # FM-index share: select+expand kernel (rank kernel of the metric), algorithmic bytes unknown per
-    # trace here -> report time share; tools/fm_microbench.py reports GB/s on recorded traces.
+            "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus,
+            "traffic": TRAFFIC_PER_LAUNCH.get(args.gemm_mode),
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({which}; the kernel runs inside a long step)",
+            "avg_launch_us": prof["total_us"] / max(prof["launches"], 1), "launches_per_step": prof["launches"],
+            "share_of_step": gemm_s / (ms / args.steps * 1e-3),
+            "tensor_pipe_TFLOPs": ach * passes, "tensor_pipe_frac": ach * passes / tf_sus,
+            "note": "achieved = algorithmic 2MNK flops (fp32-equivalent) of all GEMM launches of one step / their summed "
+                    "CUDA-event durations; the kernel issues 3 half-precision tensor-core passes per product "
+                    "(error-compensated split, DESIGN.md section 4), so the tensor pipe itself runs at tensor_pipe_TFLOPs; "
+                    "traffic = dram bytes read+written per launch of the fc1-shaped GEMM (ncu, profiles/)"}
+    # ---- the metric's rank kernel: batched LF-mapping (backward_search_step) on this 10 M-token index,
+    # 4 M random (symbol, lo, hi) triples, CUDA events.  The 27 MB index is L2-resident, so this is L2,
+    # not HBM, bandwidth; the beyond-L2 figure is in profiles/r01_fm_microbench_v3_bigindex.json.
+    Nlf = 1 << 22
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    sym = torch.randint(14, 50000, (Nlf,), device=dev, generator=g)
+    lo_t = torch.randint(0, index.size() // 2, (Nlf,), device=dev, generator=g)
+    hi_t = lo_t + torch.randint(1, index.size() // 2, (Nlf,), device=dev, generator=g)
+    for _ in range(3):
+        index.lf_step_tensors(sym, lo_t, hi_t)
+    ea = torch.cuda.Event(enable_timing=True); eb = torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(10):
+        index.lf_step_tensors(sym, lo_t, hi_t)
+    eb.record(); torch.cuda.synchronize()
+    lf_s = ea.elapsed_time(eb) * 1e-3 / 10
+    rank_kernel = {"kernel": "lf_step_kernel", "triples": Nlf, "us": lf_s * 1e6, "steps_per_s": Nlf / lf_s,
+                   "algorithmic_GBps": Nlf * 48 * 16 / lf_s / 1e9, "hbm_peak_GBps": hbm,
+                   "frac_of_hbm_peak": Nlf * 48 * 16 / lf_s / 1e9 / hbm,
+                   "note": "48*L B per LF step (SURVEY 8d); index L2-resident at 10 M tokens; "
+                           "select+expand phase of the step: %.1f ms of %.1f ms" % (phases["select_expand"] / 1e3, phases["total"] / 1e3)}
     out = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -217,7 +245,7 @@ def run_ours(args):
                       "parallelism": f"query-sharded x{world}, index+weights replicated, one NCCL gather",
                       "l2": "per-step working set (KV cache + logits > 10 GB) exceeds L2; no explicit flush"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-           "roofline": roof, "phases_us_last_step": phases,
+           "roofline": roof, "rank_kernel": rank_kernel, "phases_us_last_step": phases,
            "cpu_baseline": cpu_baseline_sample(args)}
     print(json.dumps(out))
     if world > 1:

@@ -136,6 +136,11 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
                        const float* bias, float* C, int32_t gelu, int32_t iters, double* avg_us);
 /* kernel launches issued by the last sealdec_generate* call on this model (own kernels only) */
 int64_t sealdec_last_launch_count(const sealbart_t* model);
+/* GEMM profiling: enable != 0 makes every following GEMM launch of this model be bracketed by CUDA
+ * events on its stream.  When total_us/launches/flops are non-NULL the call first drains the device
+ * and returns the summed device time, launch count and 2MNK flops recorded since the previous call,
+ * then clears the record. */
+int sealdec_profile_gemm(sealbart_t* model, int enable, double* total_us, int64_t* launches, double* flops);
 /* microseconds spent (CUDA events) in the last generate, split by phase:
  * 0 encoder, 1 decoder layers, 2 lm_head, 3 select+expand (FM index), 4 total */
 int sealdec_last_phase_us(const sealbart_t* model, double out5[5]);

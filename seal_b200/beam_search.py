@@ -157,6 +157,12 @@ class SealBartEngine:
         check(lib.sealdec_last_phase_us(self._h, a))
         return {"encoder": a[0], "decoder_layers": a[1], "lm_head": a[2], "select_expand": a[3], "total": a[4]}
 
+    def profile_gemm(self, enable):
+        """Enable/disable CUDA-event bracketing of every GEMM launch; returns the record so far."""
+        us = C.c_double(0); n = C.c_int64(0); fl = C.c_double(0)
+        check(lib.sealdec_profile_gemm(self._h, int(bool(enable)), C.byref(us), C.byref(n), C.byref(fl)))
+        return {"total_us": us.value, "launches": n.value, "flops": fl.value}
+
     def last_launch_count(self):
         return int(lib.sealdec_last_launch_count(self._h))
 

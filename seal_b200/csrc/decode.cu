@@ -71,6 +71,9 @@ struct sealbart {
     std::vector<void*> split_allocs;
     int64_t launches = 0;
     double phase_us[5] = {0, 0, 0, 0, 0};
+    bool profile_gemm = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+    double gemm_flops = 0;
     std::vector<cudaEvent_t> events;
 };
 
@@ -225,7 +228,21 @@ void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi
 
 // C = A W^T + b (+GELU).  gemm_mode 1: 3xTF32 tcgen05 kernel on the pre-split operands (A.hi/A.lo
 // written by the producing kernel; split here only if the producer did not).  gemm_mode 0: fp32 SIMT.
+void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu);
+
 void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
+    sealbart* m = cx.m;
+    if (!m->profile_gemm || M == 0) { gemm_impl(cx, M, N, K, A, lda, l, C, ldc, gelu); return; }
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    CUDA_CHECK(cudaEventRecord(a, cx.s));
+    gemm_impl(cx, M, N, K, A, lda, l, C, ldc, gelu);
+    CUDA_CHECK(cudaEventRecord(b, cx.s));
+    m->gemm_events.emplace_back(a, b);
+    m->gemm_flops += 2.0 * (double)M * N * K;
+}
+
+void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
     if (M == 0) return;
     sealbart* m = cx.m;
     if (m->cfg.gemm_mode >= 3 && K % UK16 == 0 && lda == K && l.w_h1) {
@@ -692,6 +709,22 @@ int sealdec_last_phase_us(const sealbart_t* mc, double out5[5]) {
 }
 
 int64_t sealdec_last_launch_count(const sealbart_t* m) { return m ? m->launches : 0; }
+
+int sealdec_profile_gemm(sealbart_t* m, int enable, double* total_us, int64_t* launches, double* flops) {
+    return guarded([&] {
+        if (!m) throw ApiError(SEALFM_EINVAL, "null model");
+        CUDA_CHECK(cudaSetDevice(m->device));
+        if (total_us && launches && flops) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            double us = 0;
+            for (auto& e : m->gemm_events) { float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e.first, e.second)); us += (double)ms * 1e3; }
+            *total_us = us; *launches = (int64_t)m->gemm_events.size(); *flops = m->gemm_flops;
+        }
+        for (auto& e : m->gemm_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        m->gemm_events.clear(); m->gemm_flops = 0;
+        m->profile_gemm = enable != 0;
+    });
+}
 
 int sealdec_generate(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_host, const sealdec_params_t* p,
                      const int64_t* ids, const int64_t* mask, int64_t Q, int64_t S, float* o_score, int32_t* o_len,
