@@ -265,8 +265,8 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;
         int* ovf = m->err.as<int>() + 1;
         auto launch = [&](auto kern) {
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            kern<<<ctas, UTHREADS2, SMm::kTotal, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
+            kern<<<ctas, UTHREADS2, SMm::kTotalStaged, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
         };
         if (rowb == 128) { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>); }
         else { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 64>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>); }

@@ -27,6 +27,7 @@ struct UmmaSmem {
     static constexpr int kWBytes = BN * 128;
     static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
     static constexpr int kTotal = USTAGES * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kTotalStaged = kTotal + 16 * 2048;     // + per-warp epilogue transpose buffers
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -491,6 +492,12 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     const uint32_t full0 = bars, empty0 = bars + 8 * NST;                 // smem stage barriers
     const uint32_t tfull0 = bars + 16 * NST, tempty0 = tfull0 + 16;       // 2 TMEM buffers
     const uint32_t slot = tempty0 + 16;
+    // per-epilogue-warp 2 KB transpose buffers (32 rows x 16 floats, XOR-swizzled 16-byte chunks): the
+    // TMEM load gives lane = row, but rows are ldc floats apart in memory, so storing straight from the
+    // registers touches 32 cache lines per instruction (measured: the store phase of a tile stalled the
+    // MMAs of the next tile for ~15 us, profiles/r01_ncu_f16_fc1_raw.csv: tensor pipe 49 % active);
+    // after the transpose 4 lanes cover 64 contiguous bytes of a row, 8 rows per instruction.
+    float* stage_base = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + NST * kStage + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // persistent: CTA b walks tiles b, b + gridDim.x, ...  Tile order is chosen by the host so that
     // the LARGER operand is streamed from HBM once: n fastest when the activations dominate (the
@@ -590,39 +597,59 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
-        const int row = m_tile * UM + q * 32 + lane;
-        const int nb = n_tile * BN + cg * 64;
-        if (row < M && nb < N) {
-            const int64_t roff = (int64_t)row * ldc;
+        const int row0 = m_tile * UM + q * 32;                 // this warp's 32 rows
+        const int nb = n_tile * BN + cg * 64;                  // ... and 64 columns
+        float* stg = stage_base + (warp - 4) * 512;            // 32 x 16 floats
+        if (row0 < M && nb < N) {
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                const int n = nb + j;
-                float v[4];
-                __half h1[4], h2[4];
-                int ov = 0;
+            for (int pass = 0; pass < 4; ++pass) {             // 16 columns per pass
+                // finish the values in registers (lane = row), park them transposed-friendly in smem
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float x = acc[j + u] * w_unscale + ((bias && n + u < N) ? bias[n + u] : 0.f);
-                    v[u] = GELU ? gelu_erf_u(x) : x;
-                    if (C_h1) split_half(v[u], h1[u], h2[u], &ov);
-                }
-                if (ov) atomicExch(overflow, 1);
-                if (n + 3 < N) {
-                    if (C) *reinterpret_cast<float4*>(C + roff + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    if (C_h1) {
-                        *reinterpret_cast<uint2*>(C_h1 + roff + n) = make_uint2(
-                            (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16),
-                            (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16));
-                        *reinterpret_cast<uint2*>(C_h2 + roff + n) = make_uint2(
-                            (uint32_t)__half_as_ushort(h2[0]) | ((uint32_t)__half_as_ushort(h2[1]) << 16),
-                            (uint32_t)__half_as_ushort(h2[2]) | ((uint32_t)__half_as_ushort(h2[3]) << 16));
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    float v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int n = nb + pass * 16 + j4 * 4 + u;
+                        const float x = acc[pass * 16 + j4 * 4 + u] * w_unscale + ((bias && n < N) ? bias[n] : 0.f);
+                        v[u] = GELU ? gelu_erf_u(x) : x;
                     }
-                } else {
-                    for (int u = 0; u < 4; ++u) if (n + u < N) {
-                        if (C) C[roff + n + u] = v[u];
-                        if (C_h1) { C_h1[roff + n + u] = h1[u]; C_h2[roff + n + u] = h2[u]; }
+                    const int phys = j4 ^ ((lane >> 1) & 3);
+                    *reinterpret_cast<float4*>(stg + lane * 16 + phys * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                  // 8 rows x 64 B per instruction
+                    const int rr = i * 8 + (lane >> 2), ch = lane & 3;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + rr * 16 + (ch ^ ((rr >> 1) & 3)) * 4);
+                    const int row = row0 + rr;
+                    const int n = nb + pass * 16 + ch * 4;
+                    if (row < M && n < N) {
+                        const int64_t off = (int64_t)row * ldc + n;
+                        if (n + 3 < N) {
+                            if (C) *reinterpret_cast<float4*>(C + off) = o;
+                            if (C_h1) {
+                                __half h1[4], h2[4];
+                                int ov = 0;
+                                split_half(o.x, h1[0], h2[0], &ov); split_half(o.y, h1[1], h2[1], &ov);
+                                split_half(o.z, h1[2], h2[2], &ov); split_half(o.w, h1[3], h2[3], &ov);
+                                if (ov) atomicExch(overflow, 1);
+                                *reinterpret_cast<uint2*>(C_h1 + off) = make_uint2(
+                                    (uint32_t)__half_as_ushort(h1[0]) | ((uint32_t)__half_as_ushort(h1[1]) << 16),
+                                    (uint32_t)__half_as_ushort(h1[2]) | ((uint32_t)__half_as_ushort(h1[3]) << 16));
+                                *reinterpret_cast<uint2*>(C_h2 + off) = make_uint2(
+                                    (uint32_t)__half_as_ushort(h2[0]) | ((uint32_t)__half_as_ushort(h2[1]) << 16),
+                                    (uint32_t)__half_as_ushort(h2[2]) | ((uint32_t)__half_as_ushort(h2[3]) << 16));
+                            }
+                        } else {
+                            const float vv[4] = {o.x, o.y, o.z, o.w};
+                            for (int u = 0; u < 4; ++u) if (n + u < N) {
+                                if (C) C[off + u] = vv[u];
+                                if (C_h1) { __half a, bh; int ov = 0; split_half(vv[u], a, bh, &ov); if (ov) atomicExch(overflow, 1); C_h1[off + u] = a; C_h2[off + u] = bh; }
+                            }
+                        }
                     }
                 }
+                __syncwarp();
             }
         }
         }
