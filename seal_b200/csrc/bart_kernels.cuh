@@ -308,7 +308,75 @@ __device__ __forceinline__ void store_attn(float2 o, int64_t idx, float* __restr
 // concurrently with two 16-byte loads per lane — the key count here is tiny (<= max_length), so
 // lane-per-key would leave most lanes idle.  The current position's k/v are taken from qkv (and
 // written to the cache for the later steps).
-__global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
+template <int ROUNDS>
+__device__ __forceinline__ void self_attend_head(const float* __restrict__ qp, const float* __restrict__ kc,
+                                                 const float* __restrict__ vc, const int32_t* __restrict__ arow,
+                                                 int64_t R, int d, int col, int cur_pos, int n_keys, int g,
+                                                 float4& o0, float4& o1) {
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp)), q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+    const float* kcur = qp + d; const float* vcur = qp + 2 * d;
+    // issue every K and V load of this (row, head) before any arithmetic: the rows come from HBM
+    // (the KV cache is 14 GB at R = 15 000) and nothing below depends on more than registers
+    float4 kf[ROUNDS][2], vf[ROUNDS][2];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int s = rd * 4 + g;
+        if (s < n_keys) {
+            const int64_t off = (s == cur_pos) ? 0 : ((int64_t)s * R + arow[s]) * d + col;
+            const float* kp = (s == cur_pos) ? kcur : kc + off;
+            const float* vp = (s == cur_pos) ? vcur : vc + off;
+            kf[rd][0] = __ldg(reinterpret_cast<const float4*>(kp)); kf[rd][1] = __ldg(reinterpret_cast<const float4*>(kp + 4));
+            vf[rd][0] = __ldg(reinterpret_cast<const float4*>(vp)); vf[rd][1] = __ldg(reinterpret_cast<const float4*>(vp + 4));
+        }
+    }
+    float sc[ROUNDS];
+    float mloc = -INFINITY;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int s = rd * 4 + g;
+        sc[rd] = -INFINITY;
+        if (rd * 4 < n_keys) {                                 // warp-uniform
+            float part = 0.f;
+            if (s < n_keys) {
+                const float4 k0 = kf[rd][0], k1 = kf[rd][1];
+                part = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            part += __shfl_xor_sync(0xffffffffu, part, 4);
+            if (s < n_keys) { sc[rd] = part * 0.125f; mloc = fmaxf(mloc, sc[rd]); }
+        }
+    }
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 8));
+    mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 16));
+    float lsum = 0.f;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+        const int s = rd * 4 + g;
+        if (rd * 4 < n_keys && s < n_keys) {
+            const float p = expf(sc[rd] - mloc);
+            lsum += p;
+            const float4 v0 = vf[rd][0], v1 = vf[rd][1];
+            a0.x = fmaf(p, v0.x, a0.x); a0.y = fmaf(p, v0.y, a0.y); a0.z = fmaf(p, v0.z, a0.z); a0.w = fmaf(p, v0.w, a0.w);
+            a1.x = fmaf(p, v1.x, a1.x); a1.y = fmaf(p, v1.y, a1.y); a1.z = fmaf(p, v1.z, a1.z); a1.w = fmaf(p, v1.w, a1.w);
+        }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {                        // sum the four key groups
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        a0.x += __shfl_xor_sync(0xffffffffu, a0.x, o); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, o);
+        a0.z += __shfl_xor_sync(0xffffffffu, a0.z, o); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, o);
+        a1.x += __shfl_xor_sync(0xffffffffu, a1.x, o); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, o);
+        a1.z += __shfl_xor_sync(0xffffffffu, a1.z, o); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, o);
+    }
+    const float inv = 1.0f / lsum;
+    o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
+    o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
+}
+
+template <int ROUNDS>
+__global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
                                                                const float* __restrict__ qkv, float* kc, float* vc,
                                                                const int32_t* __restrict__ anc,
                                                                float* __restrict__ out, SplitOut so) {
@@ -320,66 +388,21 @@ __global__ void __launch_bounds__(512, 2) dec_self_attn_kernel(int64_t R, int d,
     for (int h = warp; h < heads; h += blockDim.x >> 5) {
         const int col = h * kHeadDim + i8;
         const float* qp = qkv + r * 3 * d + col;
-        const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
-        const float* kcur = qp + d; const float* vcur = qp + 2 * d;
-        if (g == 0) {                                          // persist this position's k, v
-            float* kd = kc + ((int64_t)cur_pos * R + r) * d + col; float* vd = vc + ((int64_t)cur_pos * R + r) * d + col;
-            *reinterpret_cast<float4*>(kd) = *reinterpret_cast<const float4*>(kcur);
-            *reinterpret_cast<float4*>(kd + 4) = *reinterpret_cast<const float4*>(kcur + 4);
-            *reinterpret_cast<float4*>(vd) = *reinterpret_cast<const float4*>(vcur);
-            *reinterpret_cast<float4*>(vd + 4) = *reinterpret_cast<const float4*>(vcur + 4);
-        }
-        float sc[8];
-        float mloc = -INFINITY;
-#pragma unroll
-        for (int rd = 0; rd < 8; ++rd) {
-            const int s = rd * 4 + g;
-            sc[rd] = -INFINITY;
-            if (rd * 4 < n_keys) {                             // warp-uniform
-                float part = 0.f;
-                if (s < n_keys) {
-                    const float* kp = (s == cur_pos) ? kcur : kc + ((int64_t)s * R + arow[s]) * d + col;
-                    const float4 k0 = *reinterpret_cast<const float4*>(kp), k1 = *reinterpret_cast<const float4*>(kp + 4);
-                    part = q0.x * k0.x + q0.y * k0.y + q0.z * k0.z + q0.w * k0.w + q1.x * k1.x + q1.y * k1.y + q1.z * k1.z + q1.w * k1.w;
-                }
-                part += __shfl_xor_sync(0xffffffffu, part, 1);
-                part += __shfl_xor_sync(0xffffffffu, part, 2);
-                part += __shfl_xor_sync(0xffffffffu, part, 4);
-                if (s < n_keys) { sc[rd] = part * 0.125f; mloc = fmaxf(mloc, sc[rd]); }
-            }
-        }
-        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 8));
-        mloc = fmaxf(mloc, __shfl_xor_sync(0xffffffffu, mloc, 16));
-        float lsum = 0.f;
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-#pragma unroll
-        for (int rd = 0; rd < 8; ++rd) {
-            const int s = rd * 4 + g;
-            if (rd * 4 < n_keys && s < n_keys) {
-                const float p = expf(sc[rd] - mloc);
-                lsum += p;
-                const float* vp = (s == cur_pos) ? vcur : vc + ((int64_t)s * R + arow[s]) * d + col;
-                const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
-                a0.x = fmaf(p, v0.x, a0.x); a0.y = fmaf(p, v0.y, a0.y); a0.z = fmaf(p, v0.z, a0.z); a0.w = fmaf(p, v0.w, a0.w);
-                a1.x = fmaf(p, v1.x, a1.x); a1.y = fmaf(p, v1.y, a1.y); a1.z = fmaf(p, v1.z, a1.z); a1.w = fmaf(p, v1.w, a1.w);
-            }
-        }
-        // every lane of a group holds the same p's: the group sum counts each key once per lane -> use lane 0's view
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-            a0.x += __shfl_xor_sync(0xffffffffu, a0.x, o); a0.y += __shfl_xor_sync(0xffffffffu, a0.y, o);
-            a0.z += __shfl_xor_sync(0xffffffffu, a0.z, o); a0.w += __shfl_xor_sync(0xffffffffu, a0.w, o);
-            a1.x += __shfl_xor_sync(0xffffffffu, a1.x, o); a1.y += __shfl_xor_sync(0xffffffffu, a1.y, o);
-            a1.z += __shfl_xor_sync(0xffffffffu, a1.z, o); a1.w += __shfl_xor_sync(0xffffffffu, a1.w, o);
-        }
+        float4 o0, o1;
+        // rows read from the cache are never the row written below (position cur_pos), so the
+        // read-only path is safe
+        self_attend_head<ROUNDS>(qp, kc, vc, arow, R, d, col, cur_pos, n_keys, g, o0, o1);
         if (g == 0) {
-            const float inv = 1.0f / lsum;
-            const float4 o0 = make_float4(a0.x * inv, a0.y * inv, a0.z * inv, a0.w * inv);
-            const float4 o1 = make_float4(a1.x * inv, a1.y * inv, a1.z * inv, a1.w * inv);
             const int64_t idx = r * d + col;
             if (out) { *reinterpret_cast<float4*>(out + idx) = o0; *reinterpret_cast<float4*>(out + idx + 4) = o1; }
             store_split4(so, idx, o0); store_split4(so, idx + 4, o1);
+            // persist this position's k, v for the later steps
+            const float* kcur = qp + d; const float* vcur = qp + 2 * d;
+            float* kd = kc + ((int64_t)cur_pos * R + r) * d + col; float* vd = vc + ((int64_t)cur_pos * R + r) * d + col;
+            *reinterpret_cast<float4*>(kd) = __ldg(reinterpret_cast<const float4*>(kcur));
+            *reinterpret_cast<float4*>(kd + 4) = __ldg(reinterpret_cast<const float4*>(kcur + 4));
+            *reinterpret_cast<float4*>(vd) = __ldg(reinterpret_cast<const float4*>(vcur));
+            *reinterpret_cast<float4*>(vd + 4) = __ldg(reinterpret_cast<const float4*>(vcur + 4));
         }
     }
 }
@@ -395,21 +418,27 @@ struct GroupAddr {
     const int32_t* mask;                     // [n_keys], 0 = padded key
 };
 
+template <int NW, int MAXP>
 __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, int n_keys, int head_off, int64_t out_base,
                                                   int64_t out_stride, float* __restrict__ out, const SplitOut& so) {
     __shared__ float Kt[kHeadDim][33];
     __shared__ __align__(16) float Vs[32][kHeadDim];
-    __shared__ __align__(16) float q_s[16][kHeadDim];
+    __shared__ __align__(16) float q_s[NW * MAXP][kHeadDim];
     __shared__ int32_t valid_s[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (int r0 = 0; r0 < rows; r0 += nw) {                    // a pass handles nw query rows
-        const int r = r0 + warp;
-        const bool has_row = r < rows;
-        if (has_row) {
-            const float2 q2 = *reinterpret_cast<const float2*>(g.q + r * g.q_stride + head_off + 2 * lane);
-            q_s[warp][2 * lane] = q2.x; q_s[warp][2 * lane + 1] = q2.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rbase = 0; rbase < rows; rbase += NW * MAXP) {    // a group of NW*MAXP query rows per sweep over the keys
+        float m[MAXP], l[MAXP], ax[MAXP], ay[MAXP];
+        bool has[MAXP];
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) {
+            const int r = rbase + p * NW + warp;
+            has[p] = r < rows;
+            m[p] = -INFINITY; l[p] = 0.f; ax[p] = 0.f; ay[p] = 0.f;
+            if (has[p]) {
+                const float2 q2 = *reinterpret_cast<const float2*>(g.q + r * g.q_stride + head_off + 2 * lane);
+                q_s[warp * MAXP + p][2 * lane] = q2.x; q_s[warp * MAXP + p][2 * lane + 1] = q2.y;
+            }
         }
-        float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
         for (int s0 = 0; s0 < n_keys; s0 += 32) {
             __syncthreads();                                   // previous chunk fully consumed
             for (int e = threadIdx.x; e < 32 * (kHeadDim / 4); e += blockDim.x) {
@@ -424,52 +453,68 @@ __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, 
             }
             if (threadIdx.x < 32) valid_s[threadIdx.x] = (s0 + threadIdx.x < n_keys) && g.mask[s0 + threadIdx.x] != 0;
             __syncthreads();
-            if (has_row) {
-                const bool ok = valid_s[lane] != 0;
+            const bool ok = valid_s[lane] != 0;
+            const int cnt = n_keys - s0 < 32 ? n_keys - s0 : 32;
+#pragma unroll
+            for (int p = 0; p < MAXP; ++p) {
+                if (!has[p]) continue;                         // warp-uniform
+                const float* qq = q_s[warp * MAXP + p];
                 float sc = -INFINITY;
                 if (ok) {
-                    float acc = 0.f;
-#pragma unroll 16
-                    for (int i = 0; i < kHeadDim; ++i) acc = fmaf(q_s[warp][i], Kt[i][lane], acc);
-                    sc = acc * 0.125f;
-                }
-                const float mn = fmaxf(m, warp_max(sc));
-                if (mn != -INFINITY) {
-                    const float p = ok ? expf(sc - mn) : 0.f;
-                    const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
-                    l = l * corr + warp_sum(p);
-                    ax *= corr; ay *= corr;
-                    const int cnt = n_keys - s0 < 32 ? n_keys - s0 : 32;
-                    for (int j = 0; j < cnt; ++j) {
-                        const float pj = __shfl_sync(0xffffffffu, p, j);
-                        if (pj != 0.f) {
-                            const float2 vv = *reinterpret_cast<const float2*>(&Vs[j][2 * lane]);
-                            ax = fmaf(pj, vv.x, ax); ay = fmaf(pj, vv.y, ay);
-                        }
+                    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kHeadDim; i += 4) {
+                        c0 = fmaf(qq[i], Kt[i][lane], c0); c1 = fmaf(qq[i + 1], Kt[i + 1][lane], c1);
+                        c2 = fmaf(qq[i + 2], Kt[i + 2][lane], c2); c3 = fmaf(qq[i + 3], Kt[i + 3][lane], c3);
                     }
-                    m = mn;
+                    sc = ((c0 + c1) + (c2 + c3)) * 0.125f;
                 }
+                const float mn = fmaxf(m[p], warp_max(sc));
+                if (mn == -INFINITY) continue;
+                const float pr = ok ? expf(sc - mn) : 0.f;
+                const float corr = (m[p] == -INFINITY) ? 0.f : expf(m[p] - mn);
+                l[p] = l[p] * corr + warp_sum(pr);
+                float bx0 = ax[p] * corr, by0 = ay[p] * corr, bx1 = 0.f, by1 = 0.f;
+#pragma unroll 8
+                for (int j = 0; j < 32; j += 2) {
+                    const float p0 = __shfl_sync(0xffffffffu, pr, j), p1 = __shfl_sync(0xffffffffu, pr, j + 1);
+                    if (j < cnt) {                             // masked / missing keys have p == 0 and zero V rows
+                        const float2 v0 = *reinterpret_cast<const float2*>(&Vs[j][2 * lane]);
+                        const float2 v1 = *reinterpret_cast<const float2*>(&Vs[j + 1][2 * lane]);
+                        bx0 = fmaf(p0, v0.x, bx0); by0 = fmaf(p0, v0.y, by0);
+                        bx1 = fmaf(p1, v1.x, bx1); by1 = fmaf(p1, v1.y, by1);
+                    }
+                }
+                ax[p] = bx0 + bx1; ay[p] = by0 + by1;
+                m[p] = mn;
             }
         }
-        if (has_row) store_attn(make_float2(ax / l, ay / l), out_base + r * out_stride + head_off + 2 * lane, out, so);
+#pragma unroll
+        for (int p = 0; p < MAXP; ++p) {
+            const int r = rbase + p * NW + warp;
+            if (has[p]) store_attn(make_float2(ax[p] / l[p], ay[p] / l[p]), out_base + r * out_stride + head_off + 2 * lane, out, so);
+        }
+        __syncthreads();                                       // q_s is rewritten by the next row group
     }
 }
 
+constexpr int kGAttnWarps = 8, kGAttnPasses = 2;               // 16 rows per sweep, 256 threads -> 8 CTAs / SM
+
 // Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states; the `beams` rows of query
 // blockIdx.x share the keys.  grid (Q, heads).
-__global__ void __launch_bounds__(512) cross_attn_kernel(int64_t Q, int d, int heads, int beams, int S,
+__global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t Q, int d, int heads, int beams, int S,
                                                          const float* __restrict__ q, const float* __restrict__ ckv,
                                                          const int32_t* __restrict__ src_mask, float* __restrict__ out,
                                                          SplitOut so) {
     const int64_t qi = blockIdx.x;
     const int h = blockIdx.y;
     GroupAddr g{q + qi * beams * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
-    grouped_attention(g, beams, S, h * kHeadDim, qi * beams * d, d, out, so);
+    grouped_attention<kGAttnWarps, kGAttnPasses>(g, beams, S, h * kHeadDim, qi * beams * d, d, out, so);
 }
 
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).
 // qkv [Q*S][3d].  grid (Q, heads).
-__global__ void __launch_bounds__(512) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,
+__global__ void __launch_bounds__(kGAttnWarps * 32) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,
                                                             const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ src_mask,
                                                             float* __restrict__ out, SplitOut so) {
@@ -477,7 +522,7 @@ __global__ void __launch_bounds__(512) enc_self_attn_kernel(int64_t Q, int d, in
     const int h = blockIdx.y;
     const float* base = qkv + qi * S * 3 * d;
     GroupAddr g{base, 3 * d, base + d, base + 2 * d, 3 * d, src_mask + qi * S};
-    grouped_attention(g, S, S, h * kHeadDim, qi * S * d, d, out, so);
+    grouped_attention<kGAttnWarps, kGAttnPasses>(g, S, S, h * kHeadDim, qi * S * d, d, out, so);
 }
 
 }  // namespace sealb200

@@ -383,7 +383,7 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     const int heads = m->cfg.heads;
     for (auto& L : m->enc) {
         gemm(cx, Tk, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf));
+        enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, Tk, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, Tk, d, x.x, tmp.x, L.ln_attn, x);
@@ -429,13 +429,17 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         float* kc = m->kc.as<float>() + (size_t)l * D.T * R * d;
         float* vc = m->vc.as<float>() + (size_t)l * D.T * R * d;
         gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        dec_self_attn_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
-                                                                               attn.x, split_of(attn, ovf));
+        if (pos + 1 <= 12)
+            dec_self_attn_kernel<3><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                                      attn.x, split_of(attn, ovf));
+        else
+            dec_self_attn_kernel<8><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                                      attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
-        cross_attn_kernel<<<dim3((unsigned)D.Q, heads), 512, 0, cx.s>>>(D.Q, d, heads, D.B, (int)D.S, cq.x,
+        cross_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
                                                                             attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;

@@ -162,6 +162,11 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
     for (int b = 0; b < B; ++b) {
         const int64_t r = r0 + b;
         const float* lp = st.logits + r * c.ld;
+        // Exact pruning: every candidate of this row scores <= beam_score (log-probs <= 0, forced tokens
+        // add 0).  Once K candidates are held and the row's beam score is below the K-th best, nothing
+        // in the row can enter the top-K and no fill-in will be needed -> skip the row entirely,
+        // including its 200 KB of logits.  (First step: beams 1..B-1 start at -1e9, :214-216.)
+        if (S.tcount == K && st.beam_scores_in[r] < S.thr) continue;
         // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251), ONE streaming pass:
         // per-thread running (max, sum exp(x - max)), merged across the block.
         float mx = -INFINITY, se = 0.f;
