@@ -24,8 +24,10 @@ sys.path.insert(0, ROOT)
 METRIC = "queries/sec at beam=15, 1k queries, 10M-token index; rank-kernel HBM GB/s"
 BEAM, MIN_LEN, MAX_LEN, LP = 15, 10, 10, 0.0          # SEALSearcher body defaults (retrieval.py:70-83)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the fc1-shaped GEMM (M=15000, N=4096, K=1024) from
-# `ncu --set full` (profiles/r01_ncu_*_raw.csv); algorithmic bytes of that launch: A 61 MB + W 17 MB + C 246 MB.
-TRAFFIC_PER_LAUNCH = {2: 438.3e6}
+# `ncu --set full` (profiles/r01_ncu_f16_fc1_v2_raw.csv: 80.0 MB read + 210.8 MB written; r01_ncu_umma_fc1_raw.csv for
+# the TF32 kernel); algorithmic bytes of that launch: A halves 61 MB + W halves 17 MB + C halves 246 MB = 324 MB, of
+# which the activations/weights mostly hit L2 (they were just written by the producer kernel).
+TRAFFIC_PER_LAUNCH = {2: 438.3e6, 3: 290.8e6, 4: 290.8e6}
 
 
 def peaks():
