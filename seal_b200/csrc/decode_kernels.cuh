@@ -382,9 +382,24 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             uint32_t* row = st.mask_out + nr * c.mask_words;
             for (int w = lane; w < c.mask_words; w += 32) row[w] = 0;
             __syncwarp();
+            const uint64_t l = st.lo_out[nr], h = st.hi_out[nr];
+            if (h > l && h - l >= kWideRange) continue;        // wide: whole CTA below
             MaskSink sink{row, (uint32_t)V, (uint32_t)c.shift};
-            warp_expand(fm, st.lo_out[nr], st.hi_out[nr], sink, S.frontier[warp]);
+            warp_expand(fm, l, h, sink, S.frontier[warp]);
             __syncwarp();
+        }
+        __syncthreads();
+        // wide successor sets (thousands of distinct tokens): all 512 threads expand one beam at a time;
+        // the candidate staging area is free by now and holds the block frontier
+        using SelFrontier = BlockFrontierT<1024>;
+        static_assert(sizeof(SelFrontier) <= sizeof(S.cval) + sizeof(S.cidx), "frontier must fit the staging area");
+        SelFrontier& BF = *reinterpret_cast<SelFrontier*>(S.cval);
+        for (int j = 0; j < B; ++j) {
+            const int64_t nr = r0 + j;
+            const uint64_t l = st.lo_out[nr], h = st.hi_out[nr];
+            if (!(h > l && h - l >= kWideRange)) continue;     // uniform
+            MaskSink sink{st.mask_out + nr * c.mask_words, (uint32_t)V, (uint32_t)c.shift};
+            block_expand(fm, l, h, sink, BF);
         }
     }
 }

@@ -78,4 +78,62 @@ __device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sin
 }
 
 
+
+// Block-cooperative expansion for WIDE ranges (thousands of distinct successors): the warp version
+// leaves one warp walking tens of thousands of tree nodes (measured tail: 3.5 ms for one row).  Here a
+// whole CTA expands one range: level-synchronous frontier in shared memory with atomic (unordered)
+// child append until there are at least two sub-trees per thread (or the buffer is full), then every
+// thread walks its sub-trees depth-first.  Sinks must be order-independent (bitmask OR / dense counts).
+template <int CAP>
+struct BlockFrontierT {
+    static constexpr int kCap = CAP;
+    uint64_t i[2][CAP];
+    uint64_t j[2][CAP];
+    uint32_t prefix[2][CAP];
+    int count[2];
+};
+using BlockFrontier = BlockFrontierT<2048>;
+constexpr uint64_t kWideRange = 2048;       // ranges at least this wide go to the block path
+
+template <typename Sink, typename Frontier>
+__device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, Frontier& F) {
+    if (lo >= hi) return;                                      // uniform
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t L = v.L;
+    __syncthreads();
+    if (tid == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; F.count[0] = 1; F.count[1] = 0; }
+    __syncthreads();
+    int cur = 0, n = 1;
+    uint32_t level = 0;
+    while (level < L && n < 2 * nt && 2 * n <= Frontier::kCap) {
+        const int nxt = cur ^ 1;
+        for (int e = tid; e < n; e += nt) {
+            const uint64_t ei = F.i[cur][e], ej = F.j[cur][e];
+            const uint32_t ep = F.prefix[cur][e];
+            const NodeEntry ne = load_node(v, (1u << level) + ep);
+            uint64_t a, b;
+            if (ej == ei + 1) {
+                int bit;
+                a = rank1(v, ne.base + ei, &bit) - ne.ones;
+                b = a + static_cast<uint64_t>(bit);
+            } else {
+                a = rank1(v, ne.base + ei) - ne.ones;
+                b = rank1(v, ne.base + ej) - ne.ones;
+            }
+            const bool has1 = (b - a) != 0, has0 = ((ej - ei) - (b - a)) != 0;
+            const int nc = (has0 ? 1 : 0) + (has1 ? 1 : 0);
+            int w = atomicAdd(&F.count[nxt], nc);
+            if (has0) { F.i[nxt][w] = ei - a; F.j[nxt][w] = ej - b; F.prefix[nxt][w] = ep << 1; ++w; }
+            if (has1) { F.i[nxt][w] = a; F.j[nxt][w] = b; F.prefix[nxt][w] = (ep << 1) | 1u; }
+        }
+        __syncthreads();
+        n = F.count[nxt];
+        __syncthreads();
+        if (tid == 0) F.count[cur] = 0;                        // becomes the next "next"
+        cur = nxt; ++level;
+        __syncthreads();
+    }
+    for (int e = tid; e < n; e += nt) expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+    __syncthreads();
+}
 }  // namespace sealb200

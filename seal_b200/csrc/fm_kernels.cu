@@ -72,32 +72,83 @@ __global__ void __launch_bounds__(128) lf_fold_kernel(FmView v, uint64_t nq, con
 constexpr int kExpandWarps = 4;
 
 // Allowed-token bitmask rows for R ranges (seal/beam_search.py:107,131-135).  mask is zeroed here.
+// wide_list[0] = number of wide rows found, wide_list[1..] = their indices (nullptr: expand everything here)
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_mask_kernel(
     FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
-    uint32_t* __restrict__ mask, uint32_t ld_words, uint32_t vocab, uint32_t shift) {
+    uint32_t* __restrict__ mask, uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list) {
     __shared__ WarpFrontier F[kExpandWarps];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
         uint32_t* row = mask + r * ld_words;
         for (uint32_t w = lane; w < ld_words; w += 32) row[w] = 0;
         __syncwarp();
+        const uint64_t l = lo[r], h = hi[r];
+        if (wide_list && h > l && h - l >= kWideRange) {       // defer to the block-cooperative kernel
+            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[1 + k] = r; }
+            continue;
+        }
         MaskSink sink{row, vocab, shift};
-        warp_expand(v, lo[r], hi[r], sink, F[warp]);
+        warp_expand(v, l, h, sink, F[warp]);
         __syncwarp();
+    }
+}
+
+// Persistent CTAs pull the wide rows found by expand_mask_kernel (device-side list, no host sync).
+__global__ void __launch_bounds__(256) expand_mask_wide_kernel(
+    FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint32_t* __restrict__ mask,
+    uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list, unsigned long long* cursor) {
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem);
+    __shared__ unsigned long long pick;
+    const unsigned long long n = wide_list[0];
+    for (;;) {
+        if (threadIdx.x == 0) pick = atomicAdd(cursor, 1ULL);
+        __syncthreads();
+        const unsigned long long k = pick;
+        __syncthreads();
+        if (k >= n) break;
+        const uint64_t r = wide_list[1 + k];
+        MaskSink sink{mask + r * ld_words, vocab, shift};
+        block_expand(v, lo[r], hi[r], sink, F);
     }
 }
 
 // Dense per-range symbol counts (scratch for the ordered (symbol,count) API output).
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_dense_kernel(
     FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
-    uint64_t* __restrict__ dense) {
+    uint64_t* __restrict__ dense, unsigned long long* wide_list) {
     __shared__ WarpFrontier F[kExpandWarps];
-    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t stride = 1ULL << v.L;
     for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
+        const uint64_t l = lo[r], h = hi[r];
+        if (wide_list && h > l && h - l >= kWideRange) {
+            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[1 + k] = r; }
+            continue;
+        }
         DenseSink sink{dense + r * stride};
-        warp_expand(v, lo[r], hi[r], sink, F[warp]);
+        warp_expand(v, l, h, sink, F[warp]);
         __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256) expand_dense_wide_kernel(
+    FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t* __restrict__ dense,
+    unsigned long long* wide_list, unsigned long long* cursor) {
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem);
+    __shared__ unsigned long long pick;
+    const unsigned long long n = wide_list[0];
+    const uint64_t stride = 1ULL << v.L;
+    for (;;) {
+        if (threadIdx.x == 0) pick = atomicAdd(cursor, 1ULL);
+        __syncthreads();
+        const unsigned long long k = pick;
+        __syncthreads();
+        if (k >= n) break;
+        const uint64_t r = wide_list[1 + k];
+        DenseSink sink{dense + r * stride};
+        block_expand(v, lo[r], hi[r], sink, F);
     }
 }
 
@@ -348,9 +399,19 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, 
         require_device(h);
         if (!R) return;
         if ((uint64_t)ld_words * 32 < vocab) throw ApiError(SEALFM_EINVAL, "ld_words too small for vocab");
-        expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, 0, (cudaStream_t)stream>>>(
-            h->view, R, lo_d, hi_d, mask_d, ld_words, vocab, shift);
+        cudaStream_t s = (cudaStream_t)stream;
+        unsigned long long* wide = nullptr;                    // [count, rows..., cursor]
+        CUDA_CHECK(cudaMallocAsync(&wide, (R + 2) * sizeof(unsigned long long), s));
+        CUDA_CHECK(cudaMemsetAsync(wide, 0, sizeof(unsigned long long), s));
+        CUDA_CHECK(cudaMemsetAsync(wide + R + 1, 0, sizeof(unsigned long long), s));
+        expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, 0, s>>>(
+            h->view, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
         CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaFuncSetAttribute(expand_mask_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
+        expand_mask_wide_kernel<<<sm_count() * 2, 256, sizeof(BlockFrontier), s>>>(h->view, lo_d, hi_d, mask_d, ld_words, vocab, shift,
+                                                                                 wide, wide + R + 1);
+        CUDA_CHECK(cudaGetLastError());
+        CUDA_CHECK(cudaFreeAsync(wide, s));
     });
 }
 
@@ -414,7 +475,12 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             CUDA_CHECK(cudaMemcpy(dhi.p, highs + c0, cn * 8, cudaMemcpyHostToDevice));
             CUDA_CHECK(cudaMemcpy(doff.p, ub.data(), (cn + 1) * 8, cudaMemcpyHostToDevice));
             CUDA_CHECK(cudaMemset(ddense.p, 0, cn * nsym * 8));
-            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32>>>(h->view, cn, dlo.p, dhi.p, ddense.p);
+            DevBuf<unsigned long long> dwide(cn + 2);
+            CUDA_CHECK(cudaMemset(dwide.p, 0, (cn + 2) * sizeof(unsigned long long)));
+            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32>>>(h->view, cn, dlo.p, dhi.p, ddense.p, dwide.p);
+            CUDA_CHECK(cudaGetLastError());
+            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
+            expand_dense_wide_kernel<<<sm_count() * 2, 256, sizeof(BlockFrontier)>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p, dwide.p + cn + 1);
             CUDA_CHECK(cudaGetLastError());
             compact_pairs_kernel<<<(unsigned)cn, 256>>>(L, ddense.p, doff.p, dout.p, dlen.p);
             CUDA_CHECK(cudaGetLastError());
