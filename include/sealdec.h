@@ -123,6 +123,18 @@ int sealdec_generate_d(sealbart_t* model, const sealfm_t* fm, const uint32_t* oc
                        uint8_t* out_valid_d, uint64_t* out_lo_d, uint64_t* out_hi_d,
                        int32_t* error_flag_d);
 
+/* ---- teacher-forced scoring: SURVEY.md section 8(f) rank 1 ------------------------------------------
+ * The decoder pass behind rescore_keys (seal/keys.py:64-141) and compute_unigram_scores (:145-176).
+ * dec_ids: int64 [N][T] decoder inputs (row r = decoder_start + key tokens, right-padded), row r is
+ * scored against encoder input row_query[r] (sorted ascending).  HOST pointers.
+ *   out_logprob [N][T-1]: log_softmax(logits_p / temperature)[dec_ids[r][p+1]] for p = 0..T-2
+ *                         (full-vocabulary normalisation; the caller masks padding and sums, :131-135)
+ *   out_full    [N][V]  : if non-NULL, the whole log-prob vector of position out_full_pos (:167-172) */
+int sealdec_teacher_forced(sealbart_t* model, const int64_t* input_ids, const int64_t* attention_mask,
+                           int64_t Q, int64_t S, const int64_t* dec_ids, const int32_t* row_query,
+                           int64_t N, int64_t T, float temperature, float* out_logprob,
+                           int64_t out_full_pos, float* out_full);
+
 /* Test / profiling hooks: one decoder step's logits for explicit decoder inputs (teacher forcing).
  * decoder_input_ids int64 [R][t] host, R = Q*num_beams rows laid out query-major like the
  * reference's expanded batch (:517-521); writes float32 [R][V] host logits of the last position. */

@@ -500,16 +500,23 @@ __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, 
 
 constexpr int kGAttnWarps = 8, kGAttnPasses = 2;               // 16 rows per sweep, 256 threads -> 8 CTAs / SM
 
-// Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states; the `beams` rows of query
-// blockIdx.x share the keys.  grid (Q, heads).
-__global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t Q, int d, int heads, int beams, int S,
+// Cross attention: q [R][d]; ckv [Q*S][2d] (k | v) of the encoder states.  Group g (one CTA per
+// group x head) = the rows that attend to the same source: by default the `beams` rows of query g;
+// with grp_query/grp_start (ragged groups, teacher-forced re-scoring) rows grp_start[g]..grp_start[g+1]
+// of query grp_query[g].
+__global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G, int d, int heads, int beams, int S,
                                                          const float* __restrict__ q, const float* __restrict__ ckv,
-                                                         const int32_t* __restrict__ src_mask, float* __restrict__ out,
+                                                         const int32_t* __restrict__ src_mask,
+                                                         const int32_t* __restrict__ grp_query,
+                                                         const int32_t* __restrict__ grp_start, float* __restrict__ out,
                                                          SplitOut so) {
-    const int64_t qi = blockIdx.x;
+    const int64_t gi = blockIdx.x;
     const int h = blockIdx.y;
-    GroupAddr g{q + qi * beams * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
-    grouped_attention<kGAttnWarps, kGAttnPasses>(g, beams, S, h * kHeadDim, qi * beams * d, d, out, so);
+    const int64_t qi = grp_query ? grp_query[gi] : gi;
+    const int64_t row0 = grp_start ? grp_start[gi] : gi * beams;
+    const int rows = grp_start ? grp_start[gi + 1] - grp_start[gi] : beams;
+    GroupAddr g{q + row0 * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
+    grouped_attention<kGAttnWarps, kGAttnPasses>(g, rows, S, h * kHeadDim, row0 * d, d, out, so);
 }
 
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).

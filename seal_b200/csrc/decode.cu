@@ -328,7 +328,10 @@ __global__ void ids_to_tokens_kernel(int64_t R, int t, int T, const int64_t* __r
     for (int i = 0; i < T; ++i) { tokens[r * T + i] = i < t ? (int32_t)ids[r * t + i] : 0; anc[r * T + i] = (int32_t)r; }
 }
 
-struct Dims { int64_t Q, S, R; int B, T, d, f, V, ld, W; };
+struct Dims {
+    int64_t Q, S, R; int B, T, d, f, V, ld, W;
+    int64_t G = 0; const int32_t* grp_query = nullptr; const int32_t* grp_start = nullptr;   // ragged row groups (re-scoring)
+};
 
 void ensure_workspace(sealbart* m, const Dims& D) {
     const int64_t Tk = D.Q * D.S;
@@ -439,9 +442,10 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
-        cross_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, D.B, (int)D.S, cq.x,
+        const int64_t groups = D.grp_start ? D.G : D.Q;
+        cross_attn_kernel<<<dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
-                                                                            attn.x, split_of(attn, ovf));
+                                                                            D.grp_query, D.grp_start, attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
@@ -792,6 +796,72 @@ int sealdec_debug_step_logits(sealbart_t* m, const int64_t* ids, const int64_t* 
         CUDA_CHECK(cudaMemcpy2DAsync(out_logits, (size_t)D.V * 4, m->logits.p, (size_t)D.ld * 4, (size_t)D.V * 4, D.R,
                                      cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int sealdec_teacher_forced(sealbart_t* m, const int64_t* ids, const int64_t* mask, int64_t Q, int64_t S,
+                           const int64_t* dec_ids, const int32_t* row_query, int64_t N, int64_t T, float temperature,
+                           float* out_logprob, int64_t out_full_pos, float* out_full) {
+    return guarded([&] {
+        check_model(m);
+        if (!ids || !mask || !dec_ids || !row_query || N <= 0 || T < 1 || T > kMaxLen || Q <= 0 || S <= 0)
+            throw ApiError(SEALFM_EINVAL, "bad argument");
+        if (S > m->cfg.max_positions) throw ApiError(SEALFM_EINVAL, "source longer than max_positions");
+        for (int64_t r = 0; r < N; ++r) {
+            if (row_query[r] < 0 || row_query[r] >= Q || (r && row_query[r] < row_query[r - 1]))
+                throw ApiError(SEALFM_EINVAL, "row_query must be sorted and within [0, Q)");
+        }
+        const int64_t kChunk = 4096;                           // decoder rows per pass (logits: 4096 x V floats)
+        Dims D = make_dims(m, Q, S, 1, (int)T);
+        D.R = std::min<int64_t>(N, kChunk);
+        ensure_workspace(m, D);
+        cudaStream_t s = nullptr;
+        Buf d_ids, d_mask, d_dec, d_gq, d_gs, d_out, d_full;
+        struct Rel { std::vector<Buf*> v; ~Rel() { for (auto b : v) b->release(); } } rel{{&d_ids, &d_mask, &d_dec, &d_gq, &d_gs, &d_out, &d_full}};
+        d_ids.ensure(Q * S * 8); d_mask.ensure(Q * S * 8);
+        CUDA_CHECK(cudaMemcpyAsync(d_ids.p, ids, Q * S * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(d_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
+        Ctx cx{m, s};
+        m->launches = 0;
+        encoder_forward(cx, D, d_ids.as<int64_t>(), d_mask.as<int64_t>());
+        d_dec.ensure(D.R * T * 8); d_gq.ensure((D.R + 1) * 4); d_gs.ensure((D.R + 2) * 4);
+        if (T > 1) d_out.ensure(D.R * (T - 1) * 4);
+        if (out_full) d_full.ensure((size_t)D.R * D.V * 4);
+        CUDA_CHECK(cudaMemsetAsync(m->err.as<int>() + 1, 0, 4, s));
+        for (int64_t r0 = 0; r0 < N; r0 += kChunk) {
+            const int64_t rows = std::min(kChunk, N - r0);
+            std::vector<int32_t> gq, gs;
+            for (int64_t r = 0; r < rows; ++r)
+                if (r == 0 || row_query[r0 + r] != row_query[r0 + r - 1]) { gq.push_back(row_query[r0 + r]); gs.push_back((int32_t)r); }
+            gs.push_back((int32_t)rows);
+            CUDA_CHECK(cudaMemcpyAsync(d_dec.p, dec_ids + r0 * T, rows * T * 8, cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(d_gq.p, gq.data(), gq.size() * 4, cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(d_gs.p, gs.data(), gs.size() * 4, cudaMemcpyHostToDevice, s));
+            Dims C = D;
+            C.R = rows; C.G = (int64_t)gq.size(); C.grp_query = d_gq.as<int32_t>(); C.grp_start = d_gs.as<int32_t>();
+            int32_t* tk = m->st_tokens.as<int32_t>(); int32_t* an = m->st_anc.as<int32_t>();
+            ids_to_tokens_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, (int)T, (int)T, d_dec.as<int64_t>(), tk, an);
+            CUDA_CHECK(cudaGetLastError());
+            const float inv_t = 1.0f / temperature;
+            for (int p = 0; p < T; ++p) {
+                const bool need = (p + 1 < T) || (out_full && p == out_full_pos);
+                if (!need) continue;                           // the last position only feeds the full-vector output
+                decoder_step(cx, C, tk, p + 1, an, true, nullptr);
+                target_logprob_kernel<<<(unsigned)rows, 256, 0, s>>>(
+                    rows, C.V, C.ld, m->logits.as<float>(), d_dec.as<int64_t>() + (p + 1 < T ? p + 1 : 0), T, inv_t,
+                    (p + 1 < T) ? d_out.as<float>() + p : nullptr, T - 1,
+                    (out_full && p == out_full_pos) ? d_full.as<float>() : nullptr, C.V);
+                CUDA_CHECK(cudaGetLastError()); m->launches++;
+            }
+            if (T > 1 && out_logprob)
+                CUDA_CHECK(cudaMemcpyAsync(out_logprob + r0 * (T - 1), d_out.p, rows * (T - 1) * 4, cudaMemcpyDeviceToHost, s));
+            if (out_full)
+                CUDA_CHECK(cudaMemcpyAsync(out_full + (size_t)r0 * D.V, d_full.p, (size_t)rows * D.V * 4, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));              // gq/gs are stack temporaries; outputs consumed per chunk
+        }
+        int32_t ovf = 0;
+        CUDA_CHECK(cudaMemcpy(&ovf, m->err.as<int>() + 1, 4, cudaMemcpyDeviceToHost));
+        if (ovf) throw ApiError(SEALFM_EINVAL, "fp16 range exceeded in the 3xFP16 GEMM path (|x| > 65504); use gemm_mode 2 (3xTF32)");
     });
 }
 

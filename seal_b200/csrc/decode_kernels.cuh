@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         __syncthreads();
         // wide successor sets (thousands of distinct tokens): all 512 threads expand one beam at a time;
         // the candidate staging area is free by now and holds the block frontier
-        using SelFrontier = BlockFrontierT<1024>;
+        using SelFrontier = BlockFrontierT<1536>;
         static_assert(sizeof(SelFrontier) <= sizeof(S.cval) + sizeof(S.cidx), "frontier must fit the staging area");
         SelFrontier& BF = *reinterpret_cast<SelFrontier*>(S.cval);
         for (int j = 0; j < B; ++j) {
@@ -469,4 +469,32 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(int64_t R, int V, int64
     }
 }
 
+
+// ---- teacher-forced scoring (seal/keys.py:64-141 rescore_keys, :145-176 compute_unigram_scores) ------
+// out[r] = log_softmax(logits[r] / temperature)[target[r]]   (full-vocabulary normalisation);
+// optionally the whole log-prob row.  One CTA per row, single streaming pass for the statistics.
+__global__ void __launch_bounds__(256) target_logprob_kernel(int64_t R, int V, int64_t ld, const float* __restrict__ logits,
+                                                             const int64_t* __restrict__ targets, int64_t tgt_stride,
+                                                             float inv_temperature, float* __restrict__ out,
+                                                             int64_t out_stride, float* __restrict__ full, int64_t full_ld) {
+    __shared__ float red[8];
+    const int64_t r = blockIdx.x;
+    const float* lp = logits + r * ld;
+    float mx = -INFINITY, se = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float x = lp[v] * inv_temperature;
+        if (x > mx) { se *= expf(mx - x); mx = x; }
+        if (mx > -INFINITY) se += expf(x - mx);
+    }
+    const float bm = block_reduce_max(mx, red);
+    const float scaled = (mx > -INFINITY) ? se * expf(mx - bm) : 0.f;
+    const float tot = block_reduce_sum(scaled, red);
+    const float logsum = logf(tot);
+    if (out && threadIdx.x == 0) {
+        const int64_t t = targets[r * tgt_stride];
+        out[r * out_stride] = (t >= 0 && t < V) ? (lp[t] * inv_temperature - bm) - logsum : 0.f;
+    }
+    if (full)
+        for (int v = threadIdx.x; v < V; v += blockDim.x) full[r * full_ld + v] = (lp[v] * inv_temperature - bm) - logsum;
+}
 }  // namespace sealb200

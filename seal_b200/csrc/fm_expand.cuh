@@ -91,8 +91,9 @@ struct BlockFrontierT {
     uint64_t j[2][CAP];
     uint32_t prefix[2][CAP];
     int count[2];
+    int next;                       // work-queue cursor of the depth-first phase
 };
-using BlockFrontier = BlockFrontierT<2048>;
+using BlockFrontier = BlockFrontierT<1024>;   // 40 KB: five 256-thread CTAs per SM
 constexpr uint64_t kWideRange = 2048;       // ranges at least this wide go to the block path
 
 template <typename Sink, typename Frontier>
@@ -101,11 +102,11 @@ __device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& si
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint32_t L = v.L;
     __syncthreads();
-    if (tid == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; F.count[0] = 1; F.count[1] = 0; }
+    if (tid == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; F.count[0] = 1; F.count[1] = 0; F.next = 0; }
     __syncthreads();
     int cur = 0, n = 1;
     uint32_t level = 0;
-    while (level < L && n < 2 * nt && 2 * n <= Frontier::kCap) {
+    while (level < L && 2 * n <= Frontier::kCap) {             // as many sub-trees as the buffer holds
         const int nxt = cur ^ 1;
         for (int e = tid; e < n; e += nt) {
             const uint64_t ei = F.i[cur][e], ej = F.j[cur][e];
@@ -133,7 +134,12 @@ __device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& si
         cur = nxt; ++level;
         __syncthreads();
     }
-    for (int e = tid; e < n; e += nt) expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+    // sub-tree sizes differ by orders of magnitude: threads pull sub-trees from a shared cursor
+    for (;;) {
+        const int e = atomicAdd(&F.next, 1);
+        if (e >= n) break;
+        expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+    }
     __syncthreads();
 }
 }  // namespace sealb200

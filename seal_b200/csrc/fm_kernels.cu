@@ -408,7 +408,7 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, 
             h->view, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaFuncSetAttribute(expand_mask_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
-        expand_mask_wide_kernel<<<sm_count() * 2, 256, sizeof(BlockFrontier), s>>>(h->view, lo_d, hi_d, mask_d, ld_words, vocab, shift,
+        expand_mask_wide_kernel<<<sm_count() * 5, 256, sizeof(BlockFrontier), s>>>(h->view, lo_d, hi_d, mask_d, ld_words, vocab, shift,
                                                                                  wide, wide + R + 1);
         CUDA_CHECK(cudaGetLastError());
         CUDA_CHECK(cudaFreeAsync(wide, s));
@@ -480,7 +480,7 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32>>>(h->view, cn, dlo.p, dhi.p, ddense.p, dwide.p);
             CUDA_CHECK(cudaGetLastError());
             CUDA_CHECK(cudaFuncSetAttribute(expand_dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
-            expand_dense_wide_kernel<<<sm_count() * 2, 256, sizeof(BlockFrontier)>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p, dwide.p + cn + 1);
+            expand_dense_wide_kernel<<<sm_count() * 5, 256, sizeof(BlockFrontier)>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p, dwide.p + cn + 1);
             CUDA_CHECK(cudaGetLastError());
             compact_pairs_kernel<<<(unsigned)cn, 256>>>(L, ddense.p, doff.p, dout.p, dlen.p);
             CUDA_CHECK(cudaGetLastError());

@@ -114,6 +114,8 @@ def test_bart_step_logits_vs_hf_bart_large():
     dict(num_beams=3, min_length=0, max_length=6, length_penalty=0.0, forced_bos_token_id=0),
     dict(num_beams=4, min_length=0, max_length=6, length_penalty=0.0, disable_fm_index=True),
     dict(num_beams=15, min_length=10, max_length=10, length_penalty=0.0),
+    # title-style pass (seal/retrieval.py:162-176): own eos id, decoding forced to start at a document end
+    dict(num_beams=5, min_length=0, max_length=9, length_penalty=0.0, eos_token_id=777, force_decoding_from=[2]),
 ])
 def test_fm_index_generate_vs_oracle_tiny(kw):
     from oracle.decode_oracle import fm_index_generate_oracle
