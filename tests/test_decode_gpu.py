@@ -43,14 +43,18 @@ def make_inputs(rng, Q, S, vocab):
     return ids, am
 
 
-def compare_generate(ours, oracle_out, ora, tol=TOL):
+def compare_generate(ours, oracle_out, ora, tol=TOL, force=None, skip=0):
     """ours: [[(score, tokens)]], oracle_out: [[(score, tokens, constrained)]].  Compares, per query,
-    the hypotheses that survive the caller's filter (tokens found in the index)."""
+    the hypotheses that survive the caller's filter (tokens found in the index): the
+    FM-index query of a hypothesis is force_decoding_from + tokens[1 + skip:] (skip = 1 under a forced
+    BOS, which the reference drops before querying, seal/beam_search.py:71,96-101)."""
     assert len(ours) == len(oracle_out)
     worst = 0.0
+    force = list(force or [])
+    keep = lambda t: ora.get_count(force + list(t[1 + skip:])) > 0
     for q, (a, b) in enumerate(zip(ours, oracle_out)):
-        fa = sorted([(tuple(t), s) for s, t in a if ora.get_count(list(t[1:])) > 0])
-        fb = sorted([(tuple(t), s) for s, t, _ in b if ora.get_count(list(t[1:])) > 0])
+        fa = sorted([(tuple(t), s) for s, t in a if keep(t)])
+        fb = sorted([(tuple(t), s) for s, t, _ in b if keep(t)])
         assert [x[0] for x in fa] == [x[0] for x in fb], (
             f"query {q}: hypothesis token sets differ\nours-only: {sorted(set(x[0] for x in fa) - set(x[0] for x in fb))[:5]}"
             f"\noracle-only: {sorted(set(x[0] for x in fb) - set(x[0] for x in fa))[:5]}")
@@ -128,7 +132,8 @@ def test_fm_index_generate_vs_oracle_tiny(kw):
     ids, am = make_inputs(rng, Q=6, S=12, vocab=2000)
     exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
     got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
-    worst = compare_generate(got, exp, ora)
+    worst = compare_generate(got, exp, ora, force=kw.get("force_decoding_from"),
+                             skip=1 if kw.get("forced_bos_token_id") is not None else 0)
     print(f"{kw}: worst |dscore| = {worst:.3e}; hyps/query = {[len(x) for x in got]}")
     if not kw.get("disable_fm_index"):
         assert max(len(x) for x in got) > kw["num_beams"]
