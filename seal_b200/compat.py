@@ -7,7 +7,7 @@ import types
 
 
 def install():
-    from . import index, beam_search
+    from . import index, beam_search, keys
     from .cpp_modules import fm_index
     import seal_b200.cpp_modules as cppm
     seal = sys.modules.get("seal") or types.ModuleType("seal")
@@ -17,6 +17,12 @@ def install():
     sys.modules["seal"] = seal
     sys.modules["seal.index"] = index
     sys.modules["seal.beam_search"] = beam_search
+    # seal.keys keeps the reference's pure-Python evidence aggregation; only the two decoder-side
+    # helpers are replaced when the reference module is importable
+    ref_keys = sys.modules.get("seal.keys")
+    if ref_keys is not None:
+        ref_keys.rescore_keys = keys.rescore_keys
+        ref_keys.compute_unigram_scores = keys.compute_unigram_scores
     sys.modules["seal.cpp_modules"] = cppm
     sys.modules["seal.cpp_modules.fm_index"] = fm_index
     return seal
