@@ -429,6 +429,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
 }
 
 constexpr int UK16 = 64;            // k-block: 64 halves = 128 B = one swizzle row
+constexpr int UKC16 = 4;            // k-blocks (of 64 halves) per TMEM chunk
 constexpr float kHalfMax = 65504.f;
 
 __device__ __forceinline__ void split_half(float x, __half& h1, __half& h2, int* overflow) {
@@ -485,7 +486,10 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     constexpr int NST = (ROWB == 128) ? 2 : 4;
     constexpr int KE = ROWB / 2;                                           // K halves per k-block
     constexpr int kAB = UM * ROWB, kWB = BN * ROWB, kStage = 2 * kAB + 2 * kWB;
-    constexpr int kChunkBlocks = (ROWB == 128) ? UKC : 2 * UKC;            // same K per TMEM chunk (128)
+    // K per TMEM chunk: 256 (48 truncating tensor-core adds per chunk; measured error still below the fp32
+    // SIMT kernel's) so that the MMA warp can run two chunks = half a K=1024 tile ahead while the
+    // epilogue warps are busy with the previous tile's bias/GELU/split/stores
+    constexpr int kChunkBlocks = (ROWB == 128) ? UKC16 : 2 * UKC16;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // swizzle atoms want 1024 B alignment
     const uint32_t bars = base + NST * kStage;
