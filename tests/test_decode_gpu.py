@@ -104,9 +104,10 @@ def test_bart_step_logits_vs_hf_bart_large():
         lp_ref = torch.log_softmax(torch.tensor(ref), -1).numpy(); lp_got = torch.log_softmax(torch.tensor(got), -1).numpy()
         lerr = np.abs(lp_got[fin] - lp_ref[fin]).max()
         print(f"bart-large t={t}: max |dlogit| = {err:.3e}, max |dlogprob| = {lerr:.3e}")
-        # fp32 SIMT GEMM and 3xFP16 tensor-core GEMM: ~8e-6; 3xTF32 (SEALB200_GEMM=1,2): ~2e-5.  The contract is
-        # 1e-4 on summed beam scores, enforced by the generate tests below.
-        assert lerr < (1e-5 if os.environ.get("SEALB200_GEMM", "3") in ("0", "3", "4") else 4e-5), (t, err, lerr)
+        # fp32 SIMT GEMM: ~7e-6; 3xFP16 tensor-core GEMM with 256-K TMEM chunks: ~1.3e-5; 3xTF32
+        # (SEALB200_GEMM=1,2): ~2e-5.  The contract is 1e-4 on summed beam scores, enforced by the
+        # generate tests below.
+        assert lerr < (1e-5 if os.environ.get("SEALB200_GEMM", "3") == "0" else 4e-5), (t, err, lerr)
 
 
 @pytest.mark.parametrize("kw", [
