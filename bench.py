@@ -140,12 +140,12 @@ def run_ours(args):
     rec_bytes = Q * H * (4 + 4 + 4 * T + 1 + 16)
     gathered = [torch.empty_like(o_score) for _ in range(world)] if (world > 1 and rank == 0) else None
 
-    def step_device():
+    def step_device(gather=True):
         st = torch.cuda.current_stream().cuda_stream
         check(lib.sealdec_generate_d(eng._h, index._dev(), occ.data_ptr(), C.byref(p), ids.data_ptr(), mask.data_ptr(),
                                      Q, S, st, o_score.data_ptr(), o_len.data_ptr(), o_tok.data_ptr(), o_valid.data_ptr(),
                                      o_lo.data_ptr(), o_hi.data_ptr(), err.data_ptr()))
-        if world > 1:                                   # the single collective: result records to rank 0
+        if world > 1 and gather:                        # the single collective: result records to rank 0
             dist.gather(o_score, gathered, dst=0)
 
     def barrier():
@@ -192,15 +192,16 @@ def run_ours(args):
            "h2d_bytes_per_step": int(ids_np.nbytes + mask_np.nbytes + occ_np.nbytes),
            "d2h_bytes_per_step": int(rec_bytes + 4), "api": "sealdec_generate (host buffers)"}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, which = peaks()
     # ---- roofline of the dominant kernel (the decoder/encoder/lm_head GEMM), measured live: one extra
     # pass with every GEMM launch bracketed by CUDA events on its stream --------------------------------
     eng.profile_gemm(True)
-    step_device(); torch.cuda.synchronize()
+    step_device(gather=False); torch.cuda.synchronize()
     prof = eng.profile_gemm(False)
     gemm_s = prof["total_us"] * 1e-6
     passes = {0: 1, 1: 3, 2: 3, 3: 3, 4: 3}[args.gemm_mode]
@@ -248,10 +249,8 @@ def run_ours(args):
                       "l2": "per-step working set (KV cache + logits > 10 GB) exceeds L2; no explicit flush"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "roofline": roof, "rank_kernel": rank_kernel, "phases_us_last_step": phases,
-           "cpu_baseline": cpu_baseline_sample(args)}
+           "cpu_baseline": cpu_baseline_sample(args) if world == 1 else None}   # rank 0 at N = 1 only
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------
