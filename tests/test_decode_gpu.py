@@ -140,6 +140,21 @@ def test_fm_index_generate_vs_oracle_tiny(kw):
         assert max(len(x) for x in got) > kw["num_beams"]
 
 
+def test_fm_index_generate_long_wide_shapes():
+    """Shapes beyond the benchmark's: source longer than one 32-key chunk (S = 45), more beams than one
+    16-row attention sweep (20), more decoder positions than the 12-key self-attention fast path (16)."""
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200.beam_search import fm_index_generate
+    docs, ora, idx, model = tiny_setup(n_docs=600, doc_len=40)
+    rng = np.random.default_rng(9)
+    ids, am = make_inputs(rng, Q=3, S=45, vocab=2000)
+    kw = dict(num_beams=20, min_length=0, max_length=16, length_penalty=0.5)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    worst = compare_generate(got, exp, ora)
+    print(f"long/wide shapes: worst |dscore| = {worst:.3e}; hyps/query = {[len(x) for x in got]}")
+
+
 def test_fm_index_generate_sample_corpus_bart_large():
     """BASELINE.json configs[0]: the README's 3-document sample (README.md:149-153) through a fixed
     toy word->id table, 1 query, beam 5, bart-large (seeded random weights)."""
