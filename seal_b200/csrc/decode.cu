@@ -67,7 +67,7 @@ struct sealbart {
     Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
     Buf ex_hi, ex_lo, eattn_hi, eattn_lo, effn_hi, effn_lo, dx_hi, dx_lo, dattn_hi, dattn_lo, dffn_hi, dffn_lo;   // TF32 splits (gemm_mode 1)
     Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
-    Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo;
+    Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo, splitk;
     std::vector<void*> split_allocs;
     int64_t launches = 0;
     double phase_us[5] = {0, 0, 0, 0, 0};
@@ -264,9 +264,36 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         const int ctas = std::min(tiles, sm_count());
         const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;
         int* ovf = m->err.as<int>() + 1;
+        // skinny problems (a few tiles for 148 SMs): split K so that the serial K loop of a tile is spread
+        // over up to 8 CTAs, then sum the partial tiles in a fixed order
+        const int kblocks = K / (rowb / 2);
+        int k_slices = 1;
+        if (tiles * 2 <= sm_count() && kblocks >= 4) {
+            k_slices = std::min(8, std::min(kblocks / 2, sm_count() / tiles));
+            while (k_slices > 1 && kblocks % k_slices) --k_slices;
+        }
+        if (k_slices > 1) {
+            const int64_t slice_stride = (int64_t)M * ldc;
+            m->splitk.ensure((size_t)k_slices * slice_stride * 4);
+            float* part = m->splitk.as<float>();
+            const int ctas2 = std::min(tiles * k_slices, sm_count());
+            auto launch2 = [&](auto kern) {
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
+                kern<<<ctas2, UTHREADS2, SMm::kTotalStaged, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, nullptr, 1.0f, part, nullptr, nullptr,
+                                                                  ldc, n_fastest, ovf, k_slices, slice_stride);
+            };
+            if (rowb == 128) launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
+            else launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
+            if (gelu) umma_splitk_finish_kernel<true><<<fblocks, 256, 0, cx.s>>>(M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+            else umma_splitk_finish_kernel<false><<<fblocks, 256, 0, cx.s>>>(M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            return;
+        }
         auto launch = [&](auto kern) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
-            kern<<<ctas, UTHREADS2, SMm::kTotalStaged, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+            kern<<<ctas, UTHREADS2, SMm::kTotalStaged, cx.s>>>(ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf, 1, (int64_t)0);
         };
         if (rowb == 128) { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>); }
         else { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 64>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>); }
@@ -508,7 +535,7 @@ void sealbart_free(sealbart_t* m) {
                    &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->hy_score, &m->hy_len, &m->hy_tok,
                    &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms, &m->a_hi, &m->a_lo, &m->ex_hi, &m->ex_lo,
                    &m->eattn_hi, &m->eattn_lo, &m->effn_hi, &m->effn_lo, &m->dx_hi, &m->dx_lo, &m->dattn_hi, &m->dattn_lo,
-                   &m->dffn_hi, &m->dffn_lo})
+                   &m->dffn_hi, &m->dffn_lo, &m->splitk})
         b->release();
     for (auto e : m->events) cudaEventDestroy(e);
     delete m;
@@ -874,7 +901,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         sealbart fake; fake.cfg.gemm_mode = mode;
         CUDA_CHECK(cudaGetDevice(&fake.device));
         Buf dA, dW, dB, dC, whi, wlo;
-        struct Rel { std::vector<Buf*> v; sealbart* f; ~Rel() { for (auto b : v) b->release(); f->a_hi.release(); f->a_lo.release(); f->err.release(); } } rel{{&dA, &dW, &dB, &dC, &whi, &wlo}, &fake};
+        struct Rel { std::vector<Buf*> v; sealbart* f; ~Rel() { for (auto b : v) b->release(); f->a_hi.release(); f->a_lo.release(); f->err.release(); f->splitk.release(); } } rel{{&dA, &dW, &dB, &dC, &whi, &wlo}, &fake};
         const int ldc = (N + 3) / 4 * 4;
         dA.ensure((size_t)M * K * 4); dW.ensure((size_t)N * K * 4); dB.ensure((size_t)N * 4); dC.ensure((size_t)M * ldc * 4);
         CUDA_CHECK(cudaMemcpy(dA.p, A, (size_t)M * K * 4, cudaMemcpyHostToDevice));

@@ -477,7 +477,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                         int M, int N, int K, const float* __restrict__ bias, float w_unscale, float* __restrict__ C,
                         __half* __restrict__ C_h1, __half* __restrict__ C_h2, int ldc, int n_fastest,
-                        int* __restrict__ overflow) {
+                        int* __restrict__ overflow, int k_slices, int64_t slice_stride) {
     static_assert(BN == 256, "epilogue mapping assumes a 256-column tile (2 TMEM buffers = 512 columns)");
     // ROWB = bytes of K per shared-memory row: 128 -> SWIZZLE_128B, 64 K-halves per k-block, 2 stages of
     // 96 KB; 64 -> SWIZZLE_64B, 32 K-halves per k-block, 4 stages of 48 KB (three loads in flight
@@ -508,8 +508,13 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     // concurrently running CTAs then share A tiles and all of W stays in L2), m fastest when the
     // weights dominate (lm_head).
     const int m_tiles = (M + UM - 1) / UM, n_tiles = (N + BN - 1) / BN;
-    const int total_tiles = m_tiles * n_tiles;
-    const int num_k = K / KE;
+    // split-K (skinny M: a handful of tiles would leave most SMs idle and each tile's K loop is a serial
+    // chain of TMA round trips): work item = (tile, K slice); slice s accumulates k-blocks
+    // [s*num_k, (s+1)*num_k) and stores its raw fp32 partial tile at C + s*slice_stride (the caller
+    // passes bias = nullptr, w_unscale = 1, no half outputs; umma_splitk_finish_kernel sums the slices
+    // in a fixed order and applies scale / bias / GELU / split).
+    const int total_tiles = m_tiles * n_tiles * k_slices;
+    const int num_k = (K / KE) / k_slices;
     const int num_chunks = (num_k + kChunkBlocks - 1) / kChunkBlocks;
 
     if (warp == 1 && lane == 0) {
@@ -529,7 +534,8 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;                                   // k-blocks issued so far (all tiles)
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+            const int tile = item / k_slices, kb0 = (item % k_slices) * num_k;
             const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
             for (int kb = 0; kb < num_k; ++kb, ++it) {
                 const int s = it % NST;
@@ -537,10 +543,10 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 const uint32_t st = base + s * kStage;
                 mbar_expect_tx(full0 + 8 * s, kStage);
-                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * KE, m_tile * UM);
-                tma_load_2d(st + kAB, &tmA_lo, full0 + 8 * s, kb * KE, m_tile * UM);
-                tma_load_2d(st + 2 * kAB, &tmW_hi, full0 + 8 * s, kb * KE, n_tile * BN);
-                tma_load_2d(st + 2 * kAB + kWB, &tmW_lo, full0 + 8 * s, kb * KE, n_tile * BN);
+                tma_load_2d(st, &tmA_hi, full0 + 8 * s, (kb0 + kb) * KE, m_tile * UM);
+                tma_load_2d(st + kAB, &tmA_lo, full0 + 8 * s, (kb0 + kb) * KE, m_tile * UM);
+                tma_load_2d(st + 2 * kAB, &tmW_hi, full0 + 8 * s, (kb0 + kb) * KE, n_tile * BN);
+                tma_load_2d(st + 2 * kAB + kWB, &tmW_lo, full0 + 8 * s, (kb0 + kb) * KE, n_tile * BN);
             }
             }
         }
@@ -581,7 +587,9 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
         const int q = warp & 3;                                // TMEM lane quarter this warp may touch (warp % 4)
         const int cg = (warp - 4) >> 2;                        // column group: 64 columns
         uint32_t ch = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / k_slices;
+        float* Cs = C ? C + (int64_t)(item % k_slices) * slice_stride : nullptr;
         const int m_tile = n_fastest ? tile / n_tiles : tile % m_tiles, n_tile = n_fastest ? tile % n_tiles : tile / m_tiles;
         float acc[64];
 #pragma unroll
@@ -630,7 +638,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                     if (row < M && n < N) {
                         const int64_t off = (int64_t)row * ldc + n;
                         if (n + 3 < N) {
-                            if (C) *reinterpret_cast<float4*>(C + off) = o;
+                            if (Cs) *reinterpret_cast<float4*>(Cs + off) = o;
                             if (C_h1) {
                                 __half h1[4], h2[4];
                                 int ov = 0;
@@ -647,7 +655,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                         } else {
                             const float vv[4] = {o.x, o.y, o.z, o.w};
                             for (int u = 0; u < 4; ++u) if (n + u < N) {
-                                if (C) C[off + u] = vv[u];
+                                if (Cs) Cs[off + u] = vv[u];
                                 if (C_h1) { __half a, bh; int ov = 0; split_half(vv[u], a, bh, &ov); if (ov) atomicExch(overflow, 1); C_h1[off + u] = a; C_h2[off + u] = bh; }
                             }
                         }
@@ -662,6 +670,38 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     __syncthreads();
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+
+// Finishes a split-K GEMM: out = act((sum_s part[s]) * w_unscale + bias), slices summed in index order
+// (deterministic), written as fp32 and/or as the half split the next GEMM consumes.
+template <bool GELU>
+__global__ void __launch_bounds__(256) umma_splitk_finish_kernel(int64_t M, int N, int ldc, int k_slices, int64_t slice_stride,
+                                                                 const float* __restrict__ part, const float* __restrict__ bias,
+                                                                 float w_unscale, float* __restrict__ C, __half* __restrict__ C_h1,
+                                                                 __half* __restrict__ C_h2, int* __restrict__ overflow) {
+    const int64_t total = M * (int64_t)(ldc / 4);
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / (ldc / 4);
+        const int n = (int)(e % (ldc / 4)) * 4;
+        if (n >= N) continue;
+        const int64_t off = row * ldc + n;
+        float4 acc = *reinterpret_cast<const float4*>(part + off);
+        for (int sl = 1; sl < k_slices; ++sl) {
+            const float4 p = *reinterpret_cast<const float4*>(part + sl * slice_stride + off);
+            acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        }
+        float v[4] = {acc.x, acc.y, acc.z, acc.w};
+        int ov = 0;
+        for (int u = 0; u < 4; ++u) {
+            if (n + u >= N) continue;
+            float x = v[u] * w_unscale + (bias ? bias[n + u] : 0.f);
+            if (GELU) x = gelu_erf_u(x);
+            if (C) C[off + u] = x;
+            if (C_h1) { __half a, b; split_half(x, a, b, &ov); C_h1[off + u] = a; C_h2[off + u] = b; }
+        }
+        if (ov) atomicExch(overflow, 1);
     }
 }
 
