@@ -161,11 +161,16 @@ def run_ours(args):
         sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    prof_range = bool(os.environ.get("SEAL_PROFILE_RANGE"))   # ncu --profile-from-start off: capture the timed steps only
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = eng.last_launch_count() * args.steps
     phases = eng.last_phase_us()

@@ -146,6 +146,11 @@ int sealdec_debug_step_logits(sealbart_t* model, const int64_t* input_ids, const
  * device time per call (CUDA events, includes the activation split in mode 1). */
 int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A, const float* W,
                        const float* bias, float* C, int32_t gelu, int32_t iters, double* avg_us);
+/* in-kernel timeline of CTA 0 of the mode-3/4 GEMM kernel (development aid): out20 (may be NULL) receives
+ * the stamps of the last traced launch -- SM cycles at 0 entry, 1 prologue done, 2 first operands landed,
+ * 3 last MMA issued, 4 last chunk complete, 5 tile stored, 6 exit; 7/8 globaltimer ns at entry / exit --
+ * 9..16 the epilogue's four store passes (staged / stored) -- then tracing is switched on (enable != 0) or off. */
+int sealdec_debug_gemm_trace(int enable, int64_t out20[20]);
 /* kernel launches issued by the last sealdec_generate* call on this model (own kernels only) */
 int64_t sealdec_last_launch_count(const sealbart_t* model);
 /* GEMM profiling: enable != 0 makes every following GEMM launch of this model be bracketed by CUDA

@@ -103,6 +103,7 @@ _DEC_SIGS = {
     "sealdec_debug_step_logits": (i32, [vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, vp]),
     "sealdec_debug_gemm": (i32, [i32, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32,
                                  C.POINTER(C.c_double)]),
+    "sealdec_debug_gemm_trace": (i32, [i32, C.POINTER(C.c_int64)]),
     "sealdec_last_launch_count": (C.c_int64, [vp]),
     "sealdec_profile_gemm": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "sealdec_last_phase_us": (i32, [vp, C.POINTER(C.c_double)]),

@@ -268,8 +268,10 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         // over up to 8 CTAs, then sum the partial tiles in a fixed order
         const int kblocks = K / (rowb / 2);
         int k_slices = 1;
+        static const int force_slices = [] { const char* e = std::getenv("SEALB200_KSLICES"); return e ? std::atoi(e) : 0; }();
         if (tiles * 2 <= sm_count() && kblocks >= 4) {
             k_slices = std::min(8, std::min(kblocks / 2, sm_count() / tiles));
+            if (force_slices > 0) k_slices = std::min(force_slices, kblocks);     // experiments only
             while (k_slices > 1 && kblocks % k_slices) --k_slices;
         }
         if (k_slices > 1) {
@@ -740,6 +742,19 @@ int sealdec_last_phase_us(const sealbart_t* mc, double out5[5]) {
         double enc = ms(0, 1), layers = 0, head = 0, sel = 0;
         for (size_t i = 2; i + 3 < n; i += 4) { layers += ms(i, i + 1); head += ms(i + 1, i + 2); sel += ms(i + 2, i + 3); }
         out5[0] = enc; out5[1] = layers; out5[2] = head; out5[3] = sel; out5[4] = ms(0, n - 1);
+    });
+}
+
+int sealdec_debug_gemm_trace(int enable, int64_t out20[20]) {
+    return guarded([&] {
+        if (out20) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            long long h[20];
+            CUDA_CHECK(cudaMemcpyFromSymbol(h, g_gemm_trace, sizeof(h)));
+            for (int i = 0; i < 20; ++i) out20[i] = h[i];
+        }
+        const int on = enable ? 1 : 0;
+        CUDA_CHECK(cudaMemcpyToSymbol(g_gemm_trace_on, &on, sizeof(int)));
     });
 }
 

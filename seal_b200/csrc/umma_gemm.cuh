@@ -471,6 +471,19 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
+// Optional in-kernel timeline of CTA 0 (debug ABI sealdec_debug_gemm_trace): SM cycle counter at
+// 0 entry, 1 prologue done, 2 first operands landed, 3 last MMA issued, 4 last chunk complete,
+// 5 tile stored, 6 exit; 7/8 = %globaltimer (ns) at entry / exit; 9.. = epilogue sub-steps of warp 4
+// (after staging and after the stores of each of the 4 passes).
+__device__ long long g_gemm_trace[20];
+__device__ int g_gemm_trace_on;
+__device__ __forceinline__ void gemm_trace(int i) {
+    if (blockIdx.x == 0 && g_gemm_trace_on) {
+        g_gemm_trace[i] = clock64();
+        if (i == 0 || i == 6) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_gemm_trace[i == 0 ? 7 : 8] = (long long)t; }
+    }
+}
+
 template <int BN, bool GELU, int ROWB>
 __global__ void __launch_bounds__(UTHREADS2, 1)
 umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -503,6 +516,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     // after the transpose 4 lanes cover 64 contiguous bytes of a row, 8 rows per instruction.
     float* stage_base = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + NST * kStage + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) gemm_trace(0);
     // persistent: CTA b walks tiles b, b + gridDim.x, ...  Tile order is chosen by the host so that
     // the LARGER operand is streamed from HBM once: n fastest when the activations dominate (the
     // concurrently running CTAs then share A tiles and all of W stays in L2), m fastest when the
@@ -530,6 +544,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+    if (threadIdx.x == 0) gemm_trace(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -567,6 +582,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                     const int s = it % NST;
                     const uint32_t ph = (it / NST) & 1;
                     mbar_wait(full0 + 8 * s, ph);
+                    if (it == 0) gemm_trace(2);
                     tc_fence_after();
                     const uint32_t st = base + s * kStage;
                     const uint64_t a_hi = umma_desc<ROWB>(st), a_lo = umma_desc<ROWB>(st + kAB);
@@ -581,6 +597,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                 }
                 umma_commit(tfull0 + 8 * buf);                 // this chunk's partial sums are complete
             }
+            if (tile == 0) gemm_trace(3);
             }
         }
     } else if (warp >= 4) {
@@ -609,6 +626,8 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
+        const bool tr = item == 0 && warp == 4 && lane == 0;
+        if (tr) gemm_trace(4);
         const int row0 = m_tile * UM + q * 32;                 // this warp's 32 rows
         const int nb = n_tile * BN + cg * 64;                  // ... and 64 columns
         float* stg = stage_base + (warp - 4) * 512;            // 32 x 16 floats
@@ -629,6 +648,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                     *reinterpret_cast<float4*>(stg + lane * 16 + phys * 4) = make_float4(v[0], v[1], v[2], v[3]);
                 }
                 __syncwarp();
+                if (tr) gemm_trace(9 + 2 * pass);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {                  // 8 rows x 64 B per instruction
                     const int rr = i * 8 + (lane >> 2), ch = lane & 3;
@@ -662,8 +682,10 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
                     }
                 }
                 __syncwarp();
+                if (tr) gemm_trace(10 + 2 * pass);
             }
         }
+        if (tr) gemm_trace(5);
         }
     }
     tc_fence_before();
@@ -671,6 +693,7 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+    if (threadIdx.x == 0) gemm_trace(6);
 }
 
 
