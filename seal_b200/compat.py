@@ -17,12 +17,14 @@ def install():
     sys.modules["seal"] = seal
     sys.modules["seal.index"] = index
     sys.modules["seal.beam_search"] = beam_search
-    # seal.keys keeps the reference's pure-Python evidence aggregation; only the two decoder-side
-    # helpers are replaced when the reference module is importable
+    # seal.keys: the decoder-side helpers and the evidence aggregation are replaced in place when the
+    # reference module is importable (its remaining helpers -- deduplicate, decompose_query_into_keys --
+    # stay the reference's own)
     ref_keys = sys.modules.get("seal.keys")
     if ref_keys is not None:
         ref_keys.rescore_keys = keys.rescore_keys
         ref_keys.compute_unigram_scores = keys.compute_unigram_scores
+        ref_keys.aggregate_evidence = keys.aggregate_evidence
     sys.modules["seal.cpp_modules"] = cppm
     sys.modules["seal.cpp_modules.fm_index"] = fm_index
     return seal

@@ -168,6 +168,17 @@ class FMIndex:
                                                lo.ctypes.data, hi.ctypes.data))
         return lo, hi
 
+    def extract_text_batch(self, begins, ends):
+        """n intervals -> list of n uint64 arrays (one kernel launch; sealfm_extract_text)."""
+        b = _u64(begins); e = _u64(ends)
+        offs = np.zeros(len(b) + 1, dtype=np.uint64)
+        total = int((e.astype(np.int64) - b.astype(np.int64)).clip(min=0).sum())
+        out = np.zeros(max(total, 1), dtype=np.uint64)
+        check(lib.sealfm_extract_text(self._dev(), len(b), b.ctypes.data, e.ctypes.data, offs.ctypes.data,
+                                      out.ctypes.data, len(out)))
+        o = offs.astype(np.int64)
+        return [out[o[i]:o[i + 1]] for i in range(len(b))]
+
     def locate_batch(self, rows):
         r = _u64(rows); o = np.zeros(len(r), dtype=np.uint64)
         check(lib.sealfm_locate(self._dev(), len(r), r.ctypes.data, o.ctypes.data))

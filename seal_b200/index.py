@@ -151,6 +151,20 @@ class FMIndex(_FMIndex):
         check(lib.sealfm_doc_index_from_rows(self._dev(), len(r), r.ctypes.data, out.ctypes.data))
         return out
 
+    def locate_rows(self, rows):
+        """rows -> (token positions, document ids) as uint64 arrays: locate + bisect over `beginnings`
+        (index.py:77-82,90-100) for a whole batch in one launch."""
+        pos = self.locate_batch(rows)
+        b = np.asarray(self.beginnings, dtype=np.uint64)
+        return pos, (np.searchsorted(b, pos, side="right").astype(np.int64) - 1)
+
+    def get_docs(self, doc_indices):
+        """[get_doc(d) for d in doc_indices] (index.py:68-75) with one extraction launch."""
+        b = [self.beginnings[d] for d in doc_indices]; e = [self.beginnings[d + 1] for d in doc_indices]
+        if not b:
+            return []
+        return [(t.astype(np.int64) - SHIFT).tolist() for t in self.extract_text_batch(b, e)]
+
     def prefix_allowed_tokens_fn(self):
         """fairseq/GENRE-style hook named by BASELINE.json:north_star:
         prefix_allowed_tokens_fn(batch_id, input_ids) -> List[int] (index.py:128-134 semantics)."""

@@ -1,0 +1,97 @@
+"""Generates tests/golden/keys_golden.json by running the REFERENCE's own aggregate_evidence
+(/root/reference/seal/keys.py:178-497, imported unmodified; its `seal` and `more_itertools` imports are
+satisfied by stub modules -- the function only needs an object with the seal.index.FMIndex methods,
+here oracle.fm_oracle.OracleIndex on the compiled reference FM-index).  Run in the build container only:
+
+    python tests/golden/make_keys_golden.py
+
+Each case stores the corpus recipe, the inputs and the complete return value (document order, key
+order, every float) so that tests can rebuild the index and compare exactly."""
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.fm_oracle import OracleIndex  # noqa: E402
+from seal_b200.synthetic import make_corpus  # noqa: E402
+
+CORPUS = dict(n_docs=300, doc_len=30, n_phrases=400, seed=77, vocab=600)
+
+
+def load_reference_keys():
+    stub = types.ModuleType("seal"); stub.FMIndex = OracleIndex
+    mi = types.ModuleType("more_itertools"); mi.chunked = lambda it, n: (it[i:i + n] for i in range(0, len(it), n))
+    sys.modules.setdefault("seal", stub); sys.modules.setdefault("more_itertools", mi)
+    spec = importlib.util.spec_from_file_location("ref_keys", "/root/reference/seal/keys.py")
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    return mod
+
+
+def make_inputs(docs, seed, n_keys=60, vocab=600, with_unigrams=True):
+    """Keys as the decode would deliver them: n-grams cut out of documents (so they occur), a few that do
+    not occur, duplicates with different scores, single tokens; scores = negative log-probs."""
+    rng = np.random.default_rng(seed)
+    keys = []
+    for _ in range(n_keys):
+        d = int(rng.integers(0, docs.shape[0])); L = int(rng.integers(1, 7)); a = int(rng.integers(0, docs.shape[1] - L))
+        k = [int(t) for t in docs[d, a:a + L]]
+        if rng.random() < 0.1:
+            k[-1] = int(rng.integers(4, vocab))                 # probably absent from the corpus
+        keys.append((k, float(-rng.exponential(3.0) - 0.05)))
+    keys += [(list(keys[i][0]), float(keys[i][1] - 0.5)) for i in range(0, 10, 3)]     # repeated keys
+    uni = None
+    if with_unigrams:
+        z = rng.standard_normal(vocab) * 2.0
+        uni = (z - np.log(np.exp(z).sum())).tolist()
+    return keys, uni
+
+
+CASES = [
+    dict(name="default", seed=1, kw={}),
+    dict(name="no_unigrams", seed=2, kw={}, with_unigrams=False),
+    dict(name="rare_freq_split", seed=3, kw=dict(max_occurrences_1=3, n_docs_complete_score=25)),
+    dict(name="sort_by_length", seed=4, kw=dict(sort_by_length=True, max_occurrences_1=40)),
+    dict(name="sort_by_freq", seed=5, kw=dict(sort_by_freq=True, max_occurrences_1=40)),
+    dict(name="overlaps_single_key", seed=6, kw=dict(allow_overlaps=True, single_key=0.5, single_key_add_unigrams=True)),
+    dict(name="no_fm_frequency", seed=7, kw=dict(use_fm_index_frequency=False, alpha=1.5)),
+    dict(name="add_best_unigrams", seed=8, kw=dict(add_best_unigrams_to_ngrams=True, use_top_k_unigrams=50,
+                                                   length_penalty=0.1, beta=0.5, smoothing=2.0)),
+    dict(name="ignore_free_places", seed=9, kw=dict(unigrams_ignore_free_places=True, max_occurrences_2=200,
+                                                    n_docs_complete_score=10)),
+]
+
+
+def dump_result(results, all_ngrams):
+    return {"results": [[int(d), v[0], [[list(map(int, k)), s] for k, s in v[1]], [int(t) for t in v[3]],
+                         [list(map(int, v[4][0])), v[4][1]]] for d, v in results.items()],
+            "all_ngrams": [[list(map(int, k)), s] for k, s in all_ngrams.items()]}
+
+
+def main():
+    ref = load_reference_keys()
+    docs = make_corpus(**CORPUS)
+    index = OracleIndex([list(map(int, d)) for d in docs], backend="ref")
+    out = {"corpus": CORPUS, "cases": []}
+    for c in CASES:
+        keys, uni = make_inputs(docs, c["seed"], with_unigrams=c.get("with_unigrams", True))
+        kw = dict(n_docs_complete_score=40); kw.update(c["kw"])          # keep the fixture small
+        results, all_ngrams = ref.aggregate_evidence([(list(k), s) for k, s in keys], unigram_scores=uni, index=index, **kw)
+        rec = {"name": c["name"], "kw": kw, "keys": keys, "unigram_scores": uni}
+        rec.update(dump_result(results, all_ngrams))
+        print(c["name"], "docs scored:", len(rec["results"]), "keys kept:", len(rec["all_ngrams"]),
+              "top:", rec["results"][0][:2] if rec["results"] else None)
+        out["cases"].append(rec)
+    with open(os.path.join(HERE, "keys_golden.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote keys_golden.json", os.path.getsize(os.path.join(HERE, "keys_golden.json")), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""Evidence aggregation (seal/keys.py:178-497): the oracle restatement and the batched product
+implementation against fixtures produced by the REFERENCE FUNCTION ITSELF
+(tests/golden/make_keys_golden.py -> keys_golden.json): same document order, same key order, every
+float bit-identical."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from seal_b200.synthetic import make_corpus
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "keys_golden.json")
+
+
+def load_gold():
+    with open(GOLD) as f:
+        return json.load(f)
+
+
+def flatten(results, all_ngrams):
+    return ([[int(d), v[0], [[list(map(int, k)), s] for k, s in v[1]], [int(t) for t in v[3]],
+              [list(map(int, v[4][0])), v[4][1]]] for d, v in results.items()],
+            [[list(map(int, k)), s] for k, s in all_ngrams.items()])
+
+
+def case_ids():
+    return [c["name"] for c in load_gold()["cases"]]
+
+
+@pytest.mark.parametrize("name", case_ids())
+def test_oracle_restatement_matches_reference_function(name):
+    from oracle.fm_oracle import OracleIndex
+    from oracle.keys_oracle import aggregate_evidence_oracle
+    g = load_gold()
+    docs = make_corpus(**g["corpus"])
+    index = OracleIndex([list(map(int, d)) for d in docs])
+    c = next(c for c in g["cases"] if c["name"] == name)
+    res, alln = aggregate_evidence_oracle([(list(k), s) for k, s in c["keys"]], unigram_scores=c["unigram_scores"],
+                                          index=index, **c["kw"])
+    got_r, got_a = flatten(res, alln)
+    assert got_a == c["all_ngrams"]
+    assert got_r == c["results"]
+
+
+@pytest.fixture(scope="module")
+def gpu_index():
+    from seal_b200.index import FMIndex
+    g = load_gold()
+    docs = make_corpus(**g["corpus"])
+    idx = FMIndex()
+    idx.initialize([list(map(int, d)) for d in docs])
+    return idx
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", case_ids())
+def test_product_matches_reference_function(name, gpu_index):
+    from seal_b200.keys import aggregate_evidence
+    c = next(c for c in load_gold()["cases"] if c["name"] == name)
+    res, alln = aggregate_evidence([(list(k), s) for k, s in c["keys"]], unigram_scores=c["unigram_scores"],
+                                   index=gpu_index, **c["kw"])
+    got_r, got_a = flatten(res, alln)
+    assert got_a == c["all_ngrams"]
+    assert got_r == c["results"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kw", [dict(), dict(max_occurrences_1=25, sort_by_freq=True), dict(allow_overlaps=True, single_key=0.3)])
+def test_product_matches_oracle_on_larger_corpus(kw):
+    """4 000 documents, 300 keys (tensor keys as the decode returns them), default 500-document shortlist."""
+    import torch
+    from oracle.fm_oracle import OracleIndex
+    from oracle.keys_oracle import aggregate_evidence_oracle
+    from seal_b200.index import FMIndex
+    from seal_b200.keys import aggregate_evidence
+    docs = make_corpus(n_docs=4000, doc_len=40, n_phrases=3000, seed=9, vocab=3000)
+    seqs = [list(map(int, d)) for d in docs]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs)
+    rng = np.random.default_rng(3)
+    keys = []
+    for _ in range(300):
+        d = int(rng.integers(0, docs.shape[0])); L = int(rng.integers(1, 9)); a = int(rng.integers(0, docs.shape[1] - L))
+        keys.append((torch.tensor(docs[d, a:a + L].astype(np.int64)), float(-rng.exponential(4.0) - 0.01)))
+    z = rng.standard_normal(3000) * 3.0
+    uni = (z - np.log(np.exp(z).sum())).tolist()
+    exp = flatten(*aggregate_evidence_oracle(keys, unigram_scores=uni, index=ora, **kw))
+    got = flatten(*aggregate_evidence(keys, unigram_scores=uni, index=idx, **kw))
+    assert got[1] == exp[1]
+    assert [r[0] for r in got[0]] == [r[0] for r in exp[0]]
+    assert got[0] == exp[0]
+    assert len(got[0]) > 100
+
+
+class _BatchedOracleIndex:
+    """Test double: the three batched index calls aggregate_evidence makes, answered by the CPU oracle index
+    (host-logic check of the product function without a GPU)."""
+
+    def __init__(self, ora):
+        self.ora, self.beginnings = ora, ora.beginnings
+        self.calls = {"ranges": 0, "locate": 0, "docs": 0}
+
+    def __len__(self):
+        return len(self.ora)
+
+    def get_range_batch(self, seqs):
+        self.calls["ranges"] += 1
+        r = [self.ora.get_range(s) for s in seqs]
+        return np.array([a for a, _ in r], dtype=np.uint64), np.array([b for _, b in r], dtype=np.uint64)
+
+    def locate_rows(self, rows):
+        self.calls["locate"] += 1
+        pos = np.array([self.ora.locate(int(r)) for r in rows], dtype=np.uint64)
+        return pos, np.array([self.ora.get_doc_index(int(p)) for p in pos], dtype=np.int64)
+
+    def get_docs(self, ds):
+        self.calls["docs"] += 1
+        return [self.ora.get_doc(d) for d in ds]
+
+
+@pytest.mark.parametrize("name", case_ids())
+def test_product_host_logic_with_oracle_backed_index(name):
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.keys import aggregate_evidence
+    g = load_gold()
+    docs = make_corpus(**g["corpus"])
+    index = _BatchedOracleIndex(OracleIndex([list(map(int, d)) for d in docs]))
+    c = next(c for c in g["cases"] if c["name"] == name)
+    res, alln = aggregate_evidence([(list(k), s) for k, s in c["keys"]], unigram_scores=c["unigram_scores"],
+                                   index=index, **c["kw"])
+    got_r, got_a = flatten(res, alln)
+    assert got_a == c["all_ngrams"]
+    assert got_r == c["results"]
+    assert index.calls["locate"] <= 1 and index.calls["docs"] == 1 and index.calls["ranges"] <= 3
