@@ -12,8 +12,14 @@ so the same loop runs on HF BART (``HFBartStepper`` below: eager fp32 PyTorch, t
 own arithmetic for the decoder, transformers being the un-vendored dependency that owns it) and
 on synthetic logit tables in tests.
 
-Parity status: "unpinned" by the reference's own tests (it has none); the HF-4.13 processor
-semantics of SURVEY.md §H3 are restated from the 4.13 behaviour and kept switchable.
+Parity status: PINNED against the reference's own decode code.  tests/golden/make_decode_golden.py
+imports /root/reference/seal/beam_search.py unmodified (stub modules for the transformers-4.13 names
+that no longer exist, a `Bart413Adapter` for the private GenerationMixin helpers) and runs its
+fm_index_generate / constrained_beam_search / IndexBasedLogitsProcessor / BeamSearchScorerWithMemory
+beside this restatement: identical hypothesis lists in identical order, |dscore| = 0, for nine parameter
+sets; the reference's outputs are the fixture tests/golden/decode_golden.json.  What remains an
+assumption is transformers 4.13 itself (not installed): the processor list of SURVEY.md §H3 (kept
+switchable) and InfNanRemove's 4.13 form (NaN/+inf only).
 """
 import math
 from typing import Callable, List, Optional, Sequence

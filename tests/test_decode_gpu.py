@@ -140,6 +140,33 @@ def test_fm_index_generate_vs_oracle_tiny(kw):
         assert max(len(x) for x in got) > kw["num_beams"]
 
 
+@pytest.mark.parametrize("case", range(9))
+def test_fm_index_generate_vs_reference_code_fixture(case):
+    """tests/golden/decode_golden.json holds what the reference's OWN seal/beam_search.py returned (run
+    unmodified in the build container by tests/golden/make_decode_golden.py) for these inputs."""
+    import json
+    import torch
+    from oracle.decode_oracle import make_bart
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.beam_search import fm_index_generate
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import make_corpus
+    with open(os.path.join(os.path.dirname(__file__), "golden", "decode_golden.json")) as f:
+        g = json.load(f)
+    c = g["cases"][case]
+    docs = make_corpus(**g["corpus"])
+    seqs = [d.tolist() for d in docs]
+    ora = OracleIndex(seqs)
+    idx = FMIndex(); idx.initialize(seqs, in_memory=True)
+    model = make_bart(**g["model"])
+    kw = c["kw"]
+    got = fm_index_generate(model, idx, torch.tensor(c["input_ids"]), torch.tensor(c["attention_mask"]), keep_history=True, **kw)
+    exp = [[(s, t, None) for s, t in q] for q in c["hyps"]]
+    worst = compare_generate(got, exp, ora, force=kw.get("force_decoding_from"),
+                             skip=1 if kw.get("forced_bos_token_id") is not None else 0)
+    print(f"reference-code fixture {kw}: worst |dscore| = {worst:.3e}")
+
+
 def test_fm_index_generate_long_wide_shapes():
     """Shapes beyond the benchmark's: source longer than one 32-key chunk (S = 45), more beams than one
     16-row attention sweep (20), more decoder positions than the 12-key self-attention fast path (16)."""

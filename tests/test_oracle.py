@@ -81,3 +81,29 @@ def test_oracle_index_api_matches_seal_semantics():
     # locate: position of the n-gram's last token in reversed-text coordinates -> same document
     lo, hi = idx.get_range(docs[7].tolist()[2:6])
     assert 7 in {idx.get_doc_index_from_row(r) for r in range(lo, hi)}
+
+
+def _decode_gold():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "decode_golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("case", range(9))
+def test_decode_oracle_reproduces_reference_decode_outputs(case):
+    """decode_golden.json = outputs of the reference's OWN seal/beam_search.py (run unmodified by
+    tests/golden/make_decode_golden.py): same hypotheses, same order; scores to 1e-5 (the fixture was
+    produced by eager fp32 PyTorch on another CPU)."""
+    import torch
+    from oracle.decode_oracle import make_bart, fm_index_generate_oracle
+    from seal_b200.synthetic import make_corpus
+    g = _decode_gold()
+    c = g["cases"][case]
+    docs = make_corpus(**g["corpus"])
+    ora = OracleIndex([d.tolist() for d in docs])
+    model = make_bart(**g["model"])
+    out = fm_index_generate_oracle(model, ora, torch.tensor(c["input_ids"]), torch.tensor(c["attention_mask"]), **c["kw"])
+    assert len(out) == len(c["hyps"])
+    for got, exp in zip(out, c["hyps"]):
+        assert [list(t) for _, t, _ in got] == [t for _, t in exp]
+        assert max((abs(s - e[0]) for (s, _, _), e in zip(got, exp)), default=0.0) < 1e-5
