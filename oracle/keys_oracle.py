@@ -1,6 +1,8 @@
 """TEST INFRASTRUCTURE ONLY.  CPU/torch restatement of seal/keys.py:64-141 (rescore_keys) and
 :145-176 (compute_unigram_scores) for the installed transformers (the reference file imports
-`more_itertools`/`seal` and uses HF-4.13 private helpers, so it is restated, line references kept)."""
+`more_itertools`/`seal` and uses HF-4.13 private helpers, so it is restated, line references kept).
+Pinned: tests/golden/make_keys_golden.py runs the unmodified reference functions (stub modules + a proxy
+for the one private helper) beside these restatements -- |diff| = 0 -- and stores their outputs."""
 import torch
 from transformers.modeling_outputs import BaseModelOutput
 

@@ -74,6 +74,65 @@ def dump_result(results, all_ngrams):
             "all_ngrams": [[list(map(int, k)), s] for k, s in all_ngrams.items()]}
 
 
+class Model413Proxy:
+    """What seal/keys.py:64-176 needs from a transformers-4.13 BART: parameters(), config, forward, and the
+    private `_prepare_encoder_decoder_kwargs_for_generation(input_ids, kwargs)` (4.13 signature)."""
+    def __init__(self, model): self.m, self.config = model, model.config
+    def parameters(self): return self.m.parameters()
+    def __call__(self, **kw): return self.m(**kw)
+    def _prepare_encoder_decoder_kwargs_for_generation(self, input_ids, kw):
+        kw["encoder_outputs"] = self.m.get_encoder()(input_ids=input_ids, attention_mask=kw["attention_mask"], return_dict=True)
+        return kw
+
+
+def teacher_forced_cases(ref):
+    """rescore_keys / compute_unigram_scores of the reference (keys.py:64-176) on the tiny seeded BART the
+    GPU tests use; checked against oracle/keys_oracle.py and stored."""
+    import torch
+    from oracle.decode_oracle import make_bart
+    from oracle.keys_oracle import rescore_keys_oracle, compute_unigram_scores_oracle
+    MODEL = dict(seed=0, layers=2, vocab=2000, d_model=128)
+    model = make_bart(**MODEL)
+    proxy = Model413Proxy(model)
+    rng = np.random.default_rng(12)
+    inputs = [[0] + rng.integers(4, 2000, size=int(rng.integers(3, 9))).tolist() + [2] for _ in range(5)]
+    keys = []
+    for q in range(5):
+        n = int(rng.integers(0, 7)) if q != 2 else 0
+        kk = []
+        for _ in range(n):
+            toks = rng.integers(4, 2000, size=int(rng.integers(1, 8))).tolist()
+            u = rng.random()
+            if u < 0.3: toks = [0] + toks
+            if u > 0.6: toks = toks + [2]
+            kk.append((float(rng.random()), toks) if rng.random() < 0.5 else toks)
+        keys.append(kk)
+    out = {"model": MODEL, "inputs": inputs, "keys": keys, "rescore": [], "unigram": []}
+    for kw in [dict(), dict(length_penalty=1.0), dict(prefix=[7, 9]), dict(strip_from_bos=[0], strip_from_eos=[2]), dict(batch_size=3)]:
+        got = ref.rescore_keys(proxy, [list(i) for i in inputs], [list(k) for k in keys], **kw)
+        exp = rescore_keys_oracle(model, inputs, keys, **kw)
+        worst = 0.0
+        for a, b in zip(got, exp):
+            assert [k for _, k in a] == [k for _, k in b]
+            worst = max([worst] + [abs(sa - sb) for (sa, _), (sb, _) in zip(a, b)])
+        print("rescore", kw, "oracle vs reference worst |dscore|", worst)
+        assert worst < 2e-5
+        out["rescore"].append({"kw": kw, "out": [[[s, k] for s, k in q] for q in got]})
+    got0 = ref.rescore_keys(proxy, None, [list(k) for k in keys[:2]])
+    out["rescore_no_inputs"] = [[[s, k] for s, k in q] for q in got0]
+    for kw in [dict(), dict(temperature=0.7), dict(prefix=[11])]:
+        got = ref.compute_unigram_scores(proxy, [list(i) for i in inputs], None, tolist=False, **kw)
+        exp = compute_unigram_scores_oracle(model, inputs, **kw)
+        fin = torch.isfinite(exp)
+        assert torch.equal(torch.isfinite(got), fin)
+        err = float((got[fin] - exp[fin]).abs().max())
+        print("unigram", kw, "oracle vs reference max |dlogprob|", err)
+        assert err < 1e-5
+        out["unigram"].append({"kw": kw, "logprobs_head": got[:, :64].tolist(), "row_max": got.max(-1).values.tolist(),
+                               "row_argmax": got.argmax(-1).tolist()})
+    return out
+
+
 def main():
     ref = load_reference_keys()
     docs = make_corpus(**CORPUS)
@@ -88,6 +147,7 @@ def main():
         print(c["name"], "docs scored:", len(rec["results"]), "keys kept:", len(rec["all_ngrams"]),
               "top:", rec["results"][0][:2] if rec["results"] else None)
         out["cases"].append(rec)
+    out["teacher_forced"] = teacher_forced_cases(ref)
     with open(os.path.join(HERE, "keys_golden.json"), "w") as f:
         json.dump(out, f)
     print("wrote keys_golden.json", os.path.getsize(os.path.join(HERE, "keys_golden.json")), "bytes")

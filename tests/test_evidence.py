@@ -133,3 +133,54 @@ def test_product_host_logic_with_oracle_backed_index(name):
     assert got_a == c["all_ngrams"]
     assert got_r == c["results"]
     assert index.calls["locate"] <= 1 and index.calls["docs"] == 1 and index.calls["ranges"] <= 3
+
+
+# ---- teacher-forced scoring (seal/keys.py:64-176) against the reference functions' own outputs -------
+def _tf_gold():
+    return load_gold()["teacher_forced"]
+
+
+def _check_rescore(got, exp, tol):
+    assert len(got) == len(exp)
+    worst = 0.0
+    for a, b in zip(got, exp):
+        assert [list(k) for _, k in a] == [k for _, k in b]
+        worst = max([worst] + [abs(sa - sb) for (sa, _), (sb, _) in zip(a, b)])
+    assert worst < tol, worst
+    return worst
+
+
+def test_keys_oracle_reproduces_reference_rescore_and_unigram_outputs():
+    import torch
+    from oracle.decode_oracle import make_bart
+    from oracle.keys_oracle import rescore_keys_oracle, compute_unigram_scores_oracle
+    g = _tf_gold()
+    model = make_bart(**g["model"])
+    for c in g["rescore"]:
+        _check_rescore(rescore_keys_oracle(model, g["inputs"], g["keys"], **c["kw"]), c["out"], 1e-5)
+    for c in g["unigram"]:
+        lp = compute_unigram_scores_oracle(model, g["inputs"], **c["kw"])
+        head = torch.tensor(c["logprobs_head"])
+        fin = torch.isfinite(head)
+        assert torch.equal(torch.isfinite(lp[:, :64]), fin)
+        assert float((lp[:, :64][fin] - head[fin]).abs().max()) < 1e-5
+        assert lp.argmax(-1).tolist() == c["row_argmax"]
+
+
+@pytest.mark.gpu
+def test_product_rescore_and_unigram_match_reference_outputs():
+    from oracle.decode_oracle import make_bart
+    from seal_b200.keys import rescore_keys, compute_unigram_scores
+    g = _tf_gold()
+    model = make_bart(**g["model"])
+    for c in g["rescore"]:
+        w = _check_rescore(rescore_keys(model, g["inputs"], g["keys"], **c["kw"]), c["out"], 1e-4)
+        print(f"rescore vs reference fixture {c['kw']}: worst |dscore| = {w:.3e}")
+    _check_rescore(rescore_keys(model, None, g["keys"][:2]), g["rescore_no_inputs"], 1e-4)
+    for c in g["unigram"]:
+        lp = compute_unigram_scores(model, g["inputs"], tolist=False, **c["kw"])
+        head = np.array(c["logprobs_head"], dtype=np.float64)
+        fin = np.isfinite(head)
+        assert np.array_equal(np.isfinite(lp[:, :64]), fin)
+        assert np.abs(lp[:, :64][fin] - head[fin]).max() < 2e-5
+        assert np.abs(lp.max(-1) - np.array(c["row_max"])).max() < 2e-5
