@@ -291,6 +291,12 @@ class OracleIndex:
         return bisect.bisect_right(self.beginnings, token_index) - 1
     def get_doc_index_from_row(self, row):                       # index.py:96-100
         return self.get_doc_index(self.locate(row))
+    def get_token_index_from_row(self, row):                     # index.py:90-94
+        return self.locate(row)
+    def get_doc_indices(self, sequence):                         # index.py:120-126
+        s, e = self.get_range(sequence)
+        for row in range(s, e):
+            yield self.get_doc_index_from_row(row)
     def get_doc(self, doc_index):                                # index.py:68-75
         doc = self.fm.extract_text(self.beginnings[doc_index], self.beginnings[doc_index + 1])
         return [int(x) - SHIFT for x in doc]
