@@ -45,6 +45,11 @@ int         sealfm_abi_version(void);
 /* FMIndex::initialize(const vector<u64>&)            fm_index.cpp:33-41  (construct_im)
  * symbols[0..n) must be > 0; the 0 sentinel is appended internally like sdsl::construct does. */
 int sealfm_build(const uint64_t* symbols, uint64_t n, sealfm_t** out);
+/* Same index as sealfm_build (identical sections, byte for byte), constructed on CUDA device `device`:
+ * radix-sort prefix doubling -> BWT -> level-wise wavelet tree -> samples (replaces sdsl::construct_im's
+ * qsufsort + wt_int construction, sdsl/construct.hpp:120-166, sdsl/wt_int.hpp:169-256).  n + 1 < 2^31;
+ * larger texts: sealfm_build.  SEALFM_ENODEVICE without a GPU. */
+int sealfm_build_gpu(const uint64_t* symbols, uint64_t n, int device, sealfm_t** out);
 /* FMIndex::initialize_from_file(file, width)         fm_index.cpp:43-48
  * file = raw little-endian integers of `width_bytes` (1,2,4,8) each; SEAL passes 4
  * (seal/index.py:18,62,65). */

@@ -37,6 +37,18 @@ def _default_device():
     return 0
 
 
+def _build_on_gpu(n):
+    """Index construction runs on the GPU (sealfm_build_gpu) whenever one is visible and the text fits its
+    32-bit ranks; SEALB200_BUILD=host selects the host SA-IS builder (the only one without a GPU)."""
+    if os.environ.get("SEALB200_BUILD", "gpu") == "host" or n + 1 >= (1 << 31) - 8:
+        return False
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
 class FMIndex:
     """fm_index.hpp:20-43."""
 
@@ -87,10 +99,15 @@ class FMIndex:
     def initialize(self, data):                                   # fm_index.cpp:33-41
         a = _u64(data)
         out = vp()
-        check(lib.sealfm_build(a.ctypes.data, len(a), C.byref(out)))
+        if _build_on_gpu(len(a)):
+            check(lib.sealfm_build_gpu(a.ctypes.data, len(a), _default_device(), C.byref(out)))
+        else:
+            check(lib.sealfm_build(a.ctypes.data, len(a), C.byref(out)))
         self._adopt(out.value)
 
     def initialize_from_file(self, file, width):                  # fm_index.cpp:43-48
+        if int(width) in (1, 2, 4, 8) and _build_on_gpu(os.path.getsize(file) // int(width)):
+            return FMIndex.initialize(self, np.fromfile(file, dtype=f"<u{int(width)}"))   # not a subclass override
         out = vp()
         check(lib.sealfm_build_from_file(os.fsencode(file), int(width), C.byref(out)))
         self._adopt(out.value)

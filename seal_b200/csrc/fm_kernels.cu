@@ -307,6 +307,19 @@ int sealfm_build(const uint64_t* symbols, uint64_t n, sealfm_t** out) {
         *out = h.release();
     });
 }
+int sealfm_build_gpu(const uint64_t* symbols, uint64_t n, int device, sealfm_t** out) {
+    return guarded([&] {
+        if (!out || (!symbols && n)) throw ApiError(SEALFM_EINVAL, "null argument");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+            cudaGetLastError();
+            throw ApiError(SEALFM_ENODEVICE, "no such CUDA device");
+        }
+        std::unique_ptr<sealfm> h(new sealfm());
+        build_index_gpu(symbols, n, device, h->host);
+        *out = h.release();
+    });
+}
 int sealfm_build_from_file(const char* path, int width_bytes, sealfm_t** out) {
     return guarded([&] {
         if (!out || !path) throw ApiError(SEALFM_EINVAL, "null argument");

@@ -171,3 +171,64 @@ def test_properties_at_scale():
     for di in (0, 5000, 9999):
         got = fm.extract_text(di * 100, (di + 1) * 100)
         assert [g - 10 for g in got] == docs[di].tolist()
+
+
+def _build_raw(text, gpu):
+    import ctypes as C
+    from seal_b200._lib import lib, check
+    from seal_b200.cpp_modules.fm_index import FMIndex as RawFM
+    a = np.ascontiguousarray(np.asarray(text, dtype=np.uint64))
+    out = C.c_void_p()
+    if gpu:
+        check(lib.sealfm_build_gpu(a.ctypes.data, len(a), 0, C.byref(out)))
+    else:
+        check(lib.sealfm_build(a.ctypes.data, len(a), C.byref(out)))
+    fm = RawFM(); fm._adopt(out.value)
+    return fm
+
+
+def _texts():
+    from seal_b200.synthetic import make_corpus, corpus_symbols
+    rng = np.random.default_rng(17)
+    yield "one symbol", [5]
+    yield "two symbols", [9, 9]
+    for n in (31, 32, 33, 63, 64, 65, 127, 128, 129, 1000):
+        yield f"random n={n}", rng.integers(1, 40, size=n)
+    yield "single run (longest possible repeats)", np.full(5000, 7)
+    yield "period-3 text", np.tile([3, 1, 2], 3000)
+    yield "all distinct", rng.permutation(4000) + 1
+    yield "wide alphabet", rng.integers(1, 2 ** 31, size=3000)
+    yield "max symbol 2^32-1", np.array([2 ** 32 - 1, 1, 2 ** 32 - 1, 7, 1], dtype=np.uint64)
+    docs = make_corpus(n_docs=2000, doc_len=100, n_phrases=1500, seed=8)      # verbatim repeats, duplicate phrases
+    yield "phrase corpus 200k", corpus_symbols(docs)
+    dup = np.concatenate([corpus_symbols(docs[:50])] * 6)                      # whole documents repeated 6 times
+    yield "duplicated documents", dup
+
+
+def test_gpu_index_builder_matches_host_builder_section_by_section():
+    """sealfm_build_gpu (radix-sort prefix doubling, fm_build.cu) vs sealfm_build (host SA-IS): tree bits,
+    alphabet, C, SA samples and ISA samples must be identical words -- given the text they are unique, and
+    the host builder's sections are pinned against sdsl's own .fmi (tests/golden)."""
+    names = ["tree", "alphabet", "C", "sa_samples", "isa_samples"]
+    for label, text in _texts():
+        h = _build_raw(text, gpu=False); g = _build_raw(text, gpu=True)
+        assert (g.size(), ) == (h.size(), ), label
+        for w, nm in enumerate(names):
+            a, b = h.section(w), g.section(w)
+            assert a.shape == b.shape and np.array_equal(a, b), f"{label}: section {nm} differs"
+    with pytest.raises(Exception):
+        _build_raw([3, 0, 4], gpu=True)                           # symbol 0 is the sentinel
+
+
+def test_gpu_index_builder_at_benchmark_scale():
+    """10 M tokens: same sections as the host builder; prints both build times."""
+    import time
+    from seal_b200.synthetic import make_corpus, corpus_symbols
+    text = corpus_symbols(make_corpus())
+    t0 = time.perf_counter(); g = _build_raw(text, gpu=True); tg = time.perf_counter() - t0
+    t0 = time.perf_counter(); g2 = _build_raw(text, gpu=True); tg2 = time.perf_counter() - t0
+    t0 = time.perf_counter(); h = _build_raw(text, gpu=False); th = time.perf_counter() - t0
+    print(f"index build, 10 M tokens: GPU {tg:.3f} s (first call) / {tg2:.3f} s, host SA-IS {th:.3f} s")
+    for w in range(5):
+        assert np.array_equal(h.section(w), g.section(w)), w
+    del g2
