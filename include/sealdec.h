@@ -56,7 +56,7 @@ typedef struct {
     int32_t ffn_dim;           /* 4096                                         */
     int32_t max_positions;     /* 1024 (+2 learned offset)                     */
     int32_t scale_embedding;   /* 0 for bart-large                             */
-    int32_t gemm_mode;         /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = same with 64B rows / 4-stage pipeline */
+    int32_t gemm_mode;         /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = same with 64B rows / 4-stage pipeline, 5 = 3xFP16 on CTA pairs (cta_group::2, 256x256 tiles; mode 3's kernel for skinny problems) */
 } sealbart_config_t;
 
 int  sealbart_create(const sealbart_config_t* cfg, int device, sealbart_t** out);

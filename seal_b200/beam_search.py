@@ -94,10 +94,11 @@ class SealBartEngine:
     """Device-resident BART weights + workspace (include/sealdec.h `sealbart_t`)."""
 
     def __init__(self, state_dict, config, device=0, gemm_mode=None):
-        # gemm_mode: 0 = fp32 SIMT, 1 = 3xTF32 tcgen05/TMA, 2 = persistent 3xTF32, 3 = persistent 3xFP16
-        # (default; fastest, same accuracy class).  $SEALB200_GEMM overrides the default.
+        # gemm_mode: 0 = fp32 SIMT, 1 = 3xTF32 tcgen05/TMA, 2 = persistent 3xTF32, 3 = persistent 3xFP16,
+        # 4 = 3 with 64-byte rows, 5 = 3xFP16 on CTA pairs (cta_group::2; default: fastest, same accuracy
+        # class; skinny problems use mode 3's split-K kernel).  $SEALB200_GEMM overrides the default.
         if gemm_mode is None:
-            gemm_mode = int(os.environ.get("SEALB200_GEMM", "3"))
+            gemm_mode = int(os.environ.get("SEALB200_GEMM", "5"))
         self.gemm_mode = int(gemm_mode)
         d = int(config.d_model)
         self.config = config

@@ -6,6 +6,7 @@
 #include "decode_kernels.cuh"
 #include "fm_handle.hpp"
 #include "umma_gemm.cuh"
+#include "umma_gemm_2cta.cuh"
 
 #include <cuda_runtime.h>
 
@@ -27,6 +28,7 @@ struct Lin {
     __half* w_h1 = nullptr; __half* w_h2 = nullptr;        // FP16 split copies of W * 2^s (gemm_mode 3)
     float w_unscale = 1.f;                                 // 2^-s
     CUtensorMap map_hi{}, map_lo{}; bool maps_ready = false;
+    CUtensorMap map2_hi{}, map2_lo{}; bool maps2_ready = false;   // 128-row boxes: one CTA's half of a pair's W tile (gemm_mode 5)
 };
 struct LNp { float* g = nullptr; float* b = nullptr; };
 struct EncLayerW { Lin qkv, o, fc1, fc2; LNp ln_attn, ln_final; };
@@ -246,7 +248,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
     if (M == 0) return;
     sealbart* m = cx.m;
     if (m->cfg.gemm_mode >= 3 && K % UK16 == 0 && lda == K && l.w_h1) {
-        const int rowb = m->cfg.gemm_mode == 4 ? 64 : 128;
+        const int rowb = m->cfg.gemm_mode == 4 ? 64 : 128;      // mode 5 (CTA pairs) shares mode 3's operand layout
         // 3xFP16 on tcgen05 (persistent); operands pre-split into halves by the producers
         const __half* a1 = A.h1; const __half* a2 = A.h2;
         if (!a1) {
@@ -273,6 +275,21 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             k_slices = std::min(8, std::min(kblocks / 2, sm_count() / tiles));
             if (force_slices > 0) k_slices = std::min(force_slices, kblocks);     // experiments only
             while (k_slices > 1 && kblocks % k_slices) --k_slices;
+        }
+        if (m->cfg.gemm_mode == 5 && k_slices == 1 && M > UM) {
+            // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2) on 256 x 256 tiles: a third less operand
+            // traffic out of L2 per MMA than the one-CTA kernel (umma_gemm_2cta.cuh)
+            if (!l.maps2_ready) { make_map(&l.map2_hi, l.w_h1, N, K, K, 128, true, 128); make_map(&l.map2_lo, l.w_h2, N, K, K, 128, true, 128); l.maps2_ready = true; }
+            const int m_tiles = (int)((M + UM - 1) / UM), n_tiles = (N + kUmmaBN - 1) / kUmmaBN;
+            const int pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
+            const int pairs = std::min(pair_tiles, sm_count() / 2);
+            auto launchp = [&](auto kern) {
+                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM));
+                kern<<<2 * pairs, UTHREADS2, U2_SMEM, cx.s>>>(ma1, ma2, l.map2_hi, l.map2_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+            };
+            if (gelu) launchp(umma_gemm_f16x3_2cta_kernel<true>); else launchp(umma_gemm_f16x3_2cta_kernel<false>);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            return;
         }
         if (k_slices > 1) {
             const int64_t slice_stride = (int64_t)M * ldc;

@@ -107,7 +107,7 @@ def test_bart_step_logits_vs_hf_bart_large():
         # fp32 SIMT GEMM: ~7e-6; 3xFP16 tensor-core GEMM with 256-K TMEM chunks: ~1.3e-5; 3xTF32
         # (SEALB200_GEMM=1,2): ~2e-5.  The contract is 1e-4 on summed beam scores, enforced by the
         # generate tests below.
-        assert lerr < (1e-5 if os.environ.get("SEALB200_GEMM", "3") == "0" else 4e-5), (t, err, lerr)
+        assert lerr < (1e-5 if os.environ.get("SEALB200_GEMM", "5") == "0" else 4e-5), (t, err, lerr)
 
 
 @pytest.mark.parametrize("kw", [
@@ -165,6 +165,22 @@ def test_fm_index_generate_vs_reference_code_fixture(case):
     worst = compare_generate(got, exp, ora, force=kw.get("force_decoding_from"),
                              skip=1 if kw.get("forced_bos_token_id") is not None else 0)
     print(f"reference-code fixture {kw}: worst |dscore| = {worst:.3e}")
+
+
+def test_fm_index_generate_many_rows_tiny():
+    """40 queries x 8 beams = 320 live rows: more than one 128-row GEMM tile, so the default GEMM (CTA pairs,
+    gemm_mode 5) runs its cta_group::2 kernel inside the decode loop (odd number of row tiles: the last
+    pair has an empty second CTA)."""
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200.beam_search import fm_index_generate
+    docs, ora, idx, model = tiny_setup()
+    rng = np.random.default_rng(21)
+    ids, am = make_inputs(rng, Q=40, S=14, vocab=2000)
+    kw = dict(num_beams=8, min_length=3, max_length=8, length_penalty=0.0)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    worst = compare_generate(got, exp, ora)
+    print(f"many rows: worst |dscore| = {worst:.3e}; hyps/query = {len(got[0])}")
 
 
 def test_fm_index_generate_long_wide_shapes():

@@ -34,6 +34,17 @@ SHAPES = [(5, 128, 128, False), (77, 384, 128, False), (300, 1024, 1024, False),
           (513, 1024, 4096, False), (200, 1003, 1024, False), (6, 50265, 1024, False)]
 
 
+# gemm_mode 5 (CTA pairs, cta_group::2) takes over once a problem fills the machine; these shapes do (odd and
+# even numbers of 128-row tiles, ragged N, K = 4096, GELU epilogue), the small SHAPES run its split-K fallback
+SHAPES_PAIR = [(2600, 1024, 1024, False), (1300, 4096, 1024, True), (2400, 1003, 4096, False), (700, 50265, 1024, False),
+               (1024, 3072, 1024, False)]
+
+
+@pytest.mark.parametrize("M,N,K,gelu", SHAPES_PAIR + SHAPES[:4])
+def test_gemm_cta_pair_matches_float64(M, N, K, gelu):
+    test_gemm_matches_float64(5, M, N, K, gelu)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("M,N,K,gelu", SHAPES)
 def test_gemm_matches_float64(mode, M, N, K, gelu):
@@ -56,6 +67,6 @@ def test_gemm_throughput_report():
     for (M, N, K) in [(15000, 4096, 1024), (15000, 1024, 4096), (15000, 3072, 1024), (3000, 50265, 1024)]:
         A = rng.standard_normal((M, K)).astype(np.float32); W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
         b = np.zeros(N, dtype=np.float32)
-        for mode in (0, 1, 2, 3, 4):
+        for mode in (0, 1, 2, 3, 4, 5):
             _, us = run_gemm(mode, A, W, b, False, iters=5)
             print(f"GEMM {M}x{N}x{K} mode {mode}: {us:.1f} us, {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (fp32-equivalent)")
