@@ -27,7 +27,7 @@ BEAM, MIN_LEN, MAX_LEN, LP = 15, 10, 10, 0.0          # SEALSearcher body defaul
 # `ncu --set full` (profiles/r01_ncu_f16_fc1_v2_raw.csv: 80.0 MB read + 210.8 MB written; r01_ncu_umma_fc1_raw.csv for
 # the TF32 kernel); algorithmic bytes of that launch: A halves 61 MB + W halves 17 MB + C halves 246 MB = 324 MB, of
 # which the activations/weights mostly hit L2 (they were just written by the producer kernel).
-TRAFFIC_PER_LAUNCH = {2: 438.3e6, 3: 290.8e6, 4: 290.8e6}
+TRAFFIC_PER_LAUNCH = {2: 438.3e6, 3: 290.8e6, 4: 290.8e6, 5: 292.1e6}   # dram read+write of the fc1-shaped launch (ncu --set full, profiles/)
 
 
 def peaks():

@@ -519,6 +519,104 @@ __global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G,
     grouped_attention<kGAttnWarps, kGAttnPasses>(g, rows, S, h * kHeadDim, row0 * d, d, out, so);
 }
 
+// Cross attention for sources of at most 32 positions (every decode shape of the benchmark: S <= 28): one CTA of
+// 128 threads per (group, head) stages K (padded rows: conflict-free 16-byte reads with lane = key), V, and
+// blocks of 16 query rows in shared memory; scores are register-tiled 4 rows x 1 key per thread (one K read
+// feeds four rows), the softmax runs over the lanes of a warp, and the P.V product is tiled 4 rows x 2 head
+// dims per thread.  About half the instructions per (group, head) of grouped_attention, whose one-row-per-warp
+// sweep spends two shared-memory reads per FMA (profiles/r01_SUMMARY.md).  Same ragged-group arguments as
+// cross_attn_kernel.
+constexpr int kXKeys = 32, kXRows = 16, kXPad = kHeadDim + 4;
+__global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d, int heads, int beams, int S,
+                                                               const float* __restrict__ q, const float* __restrict__ ckv,
+                                                               const int32_t* __restrict__ src_mask,
+                                                               const int32_t* __restrict__ grp_query,
+                                                               const int32_t* __restrict__ grp_start, float* __restrict__ out,
+                                                               SplitOut so) {
+    __shared__ __align__(16) float Ks[kXKeys][kXPad];
+    __shared__ __align__(16) float Vs[kXKeys][kHeadDim];
+    __shared__ __align__(16) float Qs[kXRows][kHeadDim];
+    __shared__ __align__(16) float Ps[kXRows][kXKeys];
+    __shared__ float Ls[kXRows];
+    const int64_t gi = blockIdx.x;
+    const int head_off = blockIdx.y * kHeadDim;
+    const int64_t qi = grp_query ? grp_query[gi] : gi;
+    const int64_t row0 = grp_start ? grp_start[gi] : gi * beams;
+    const int rows = grp_start ? grp_start[gi + 1] - grp_start[gi] : beams;
+    const float* kbase = ckv + qi * S * 2 * d + head_off;
+    const float* vbase = kbase + d;
+    const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
+    for (int e = tid; e < kXKeys * (kHeadDim / 4); e += 128) {
+        const int sidx = e / (kHeadDim / 4), i4 = e % (kHeadDim / 4);
+        float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+        if (sidx < S) {
+            kk = *reinterpret_cast<const float4*>(kbase + (int64_t)sidx * 2 * d + 4 * i4);
+            vv = *reinterpret_cast<const float4*>(vbase + (int64_t)sidx * 2 * d + 4 * i4);
+        }
+        *reinterpret_cast<float4*>(&Ks[sidx][4 * i4]) = kk;
+        *reinterpret_cast<float4*>(&Vs[sidx][4 * i4]) = vv;        // rows >= S stay zero: their weight is 0, never 0 * garbage
+    }
+    const bool key_ok = lane < S && src_mask[qi * S + (lane < S ? lane : 0)] != 0;
+    for (int rbase = 0; rbase < rows; rbase += kXRows) {
+        __syncthreads();                                           // K/V staged; previous block's Qs / Ps consumed
+        for (int e = tid; e < kXRows * (kHeadDim / 4); e += 128) {
+            const int r = e / (kHeadDim / 4), i4 = e % (kHeadDim / 4);
+            float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rbase + r < rows) qq = *reinterpret_cast<const float4*>(q + (row0 + rbase + r) * d + head_off + 4 * i4);
+            *reinterpret_cast<float4*>(&Qs[r][4 * i4]) = qq;
+        }
+        __syncthreads();
+        // scores: this thread = key `lane` x rows rg*4 .. rg*4+3
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i4 = 0; i4 < kHeadDim / 4; ++i4) {
+            const float4 kk = *reinterpret_cast<const float4*>(&Ks[lane][4 * i4]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 qq = *reinterpret_cast<const float4*>(&Qs[rg * 4 + u][4 * i4]);
+                c[u] = fmaf(qq.x, kk.x, c[u]); c[u] = fmaf(qq.y, kk.y, c[u]);
+                c[u] = fmaf(qq.z, kk.z, c[u]); c[u] = fmaf(qq.w, kk.w, c[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const float sc = key_ok ? c[u] * 0.125f : -INFINITY;
+            const float mx = warp_max(sc);
+            const float pr = (key_ok && mx != -INFINITY) ? expf(sc - mx) : 0.f;
+            const float sum = warp_sum(pr);
+            Ps[rg * 4 + u][lane] = pr;
+            if (lane == 0) Ls[rg * 4 + u] = sum;
+        }
+        __syncthreads();
+        // P.V: this thread = head dims 2*lane, 2*lane+1 x rows rg*4 .. rg*4+3
+        float ax[4] = {0.f, 0.f, 0.f, 0.f}, ay[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < S; j += 4) {                           // rows S..31 of Vs are zero, P there is zero
+            float4 pp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pp[u] = *reinterpret_cast<const float4*>(&Ps[rg * 4 + u][j]);
+            const float2 v0 = *reinterpret_cast<const float2*>(&Vs[j][2 * lane]);
+            const float2 v1 = *reinterpret_cast<const float2*>(&Vs[j + 1][2 * lane]);
+            const float2 v2 = *reinterpret_cast<const float2*>(&Vs[j + 2][2 * lane]);
+            const float2 v3 = *reinterpret_cast<const float2*>(&Vs[j + 3][2 * lane]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ax[u] = fmaf(pp[u].x, v0.x, ax[u]); ay[u] = fmaf(pp[u].x, v0.y, ay[u]);
+                ax[u] = fmaf(pp[u].y, v1.x, ax[u]); ay[u] = fmaf(pp[u].y, v1.y, ay[u]);
+                ax[u] = fmaf(pp[u].z, v2.x, ax[u]); ay[u] = fmaf(pp[u].z, v2.y, ay[u]);
+                ax[u] = fmaf(pp[u].w, v3.x, ax[u]); ay[u] = fmaf(pp[u].w, v3.y, ay[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = rbase + rg * 4 + u;
+            if (r < rows) {
+                const float l = Ls[rg * 4 + u];
+                store_attn(make_float2(ax[u] / l, ay[u] / l), (row0 + r) * d + head_off + 2 * lane, out, so);
+            }
+        }
+    }
+}
+
 // Encoder self attention over the S positions of the same query (bidirectional, key padding mask).
 // qkv [Q*S][3d].  grid (Q, heads).
 __global__ void __launch_bounds__(kGAttnWarps * 32) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,

@@ -283,12 +283,33 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             const int m_tiles = (int)((M + UM - 1) / UM), n_tiles = (N + kUmmaBN - 1) / kUmmaBN;
             const int pair_tiles = ((m_tiles + 1) / 2) * n_tiles;
             const int pairs = std::min(pair_tiles, sm_count() / 2);
+            // wave quantisation: when the last round of pair-tiles would keep less than half of the pairs busy, those
+            // tiles are cut into K slices (one short round instead of a full one) and summed by a finish kernel
+            int full_items = pair_tiles, tail_s = 1;
+            static const bool tail_split = [] { const char* e = std::getenv("SEALB200_TAIL_SPLIT"); return !e || std::atoi(e) != 0; }();
+            const int rem = pair_tiles % pairs;
+            if (tail_split && pair_tiles > pairs && rem > 0 && rem * 2 <= pairs) {
+                int sl = std::min(8, pairs / rem);
+                const int nk = K / 64;
+                while (sl > 1 && (nk % sl || nk / sl < 2)) --sl;
+                if (sl > 1) { tail_s = sl; full_items = pair_tiles - rem; }
+            }
+            float* part = nullptr;
+            if (tail_s > 1) { m->splitk.ensure((size_t)(pair_tiles - full_items) * tail_s * 65536 * 4); part = m->splitk.as<float>(); }
             auto launchp = [&](auto kern) {
                 CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM));
-                kern<<<2 * pairs, UTHREADS2, U2_SMEM, cx.s>>>(ma1, ma2, l.map2_hi, l.map2_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf);
+                kern<<<2 * pairs, UTHREADS2, U2_SMEM, cx.s>>>(ma1, ma2, l.map2_hi, l.map2_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf,
+                                                              full_items, tail_s, part);
             };
             if (gelu) launchp(umma_gemm_f16x3_2cta_kernel<true>); else launchp(umma_gemm_f16x3_2cta_kernel<false>);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
+            if (tail_s > 1) {
+                const int fb = (pair_tiles - full_items) * 64;
+                const int pm_tiles = (m_tiles + 1) / 2;
+                if (gelu) umma_tail_finish_kernel<true><<<fb, 256, 0, cx.s>>>((int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+                else umma_tail_finish_kernel<false><<<fb, 256, 0, cx.s>>>((int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+                CUDA_CHECK(cudaGetLastError()); m->launches++;
+            }
             return;
         }
         if (k_slices > 1) {
@@ -489,7 +510,12 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
         const int64_t groups = D.grp_start ? D.G : D.Q;
-        cross_attn_kernel<<<dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
+        if (D.S <= kXKeys)
+            cross_attn_small_kernel<<<dim3((unsigned)groups, heads), 128, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
+                                                                            m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
+                                                                            D.grp_query, D.grp_start, attn.x, split_of(attn, ovf));
+        else
+            cross_attn_kernel<<<dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
                                                                             D.grp_query, D.grp_start, attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;

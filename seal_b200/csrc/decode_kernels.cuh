@@ -170,7 +170,27 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251), ONE streaming pass:
         // per-thread running (max, sum exp(x - max)), merged across the block.
         float mx = -INFINITY, se = 0.f;
-        for (int v = tid * 4; v < V; v += kSelThreads * 4) {
+        // four 16-byte loads in flight per thread, one running-max update per 16 values (the loop is bound by
+        // load latency and instruction issue, not by HBM: profiles/r01_ncu_select_v2_raw.csv)
+        constexpr int kStride = kSelThreads * 4;
+        int v = tid * 4;
+        for (; v + 3 * kStride + 3 < V; v += 4 * kStride) {
+            const float4 a = *reinterpret_cast<const float4*>(lp + v);
+            const float4 b4 = *reinterpret_cast<const float4*>(lp + v + kStride);
+            const float4 c4 = *reinterpret_cast<const float4*>(lp + v + 2 * kStride);
+            const float4 d4 = *reinterpret_cast<const float4*>(lp + v + 3 * kStride);
+            const float m16 = fmaxf(fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(b4.x, b4.y), fmaxf(b4.z, b4.w))),
+                                    fmaxf(fmaxf(fmaxf(c4.x, c4.y), fmaxf(c4.z, c4.w)), fmaxf(fmaxf(d4.x, d4.y), fmaxf(d4.z, d4.w))));
+            if (m16 > mx) { se *= expf(mx - m16); mx = m16; }
+            if (mx > -INFINITY) {
+                const float s0 = (expf(a.x - mx) + expf(a.y - mx)) + (expf(a.z - mx) + expf(a.w - mx));
+                const float s1 = (expf(b4.x - mx) + expf(b4.y - mx)) + (expf(b4.z - mx) + expf(b4.w - mx));
+                const float s2 = (expf(c4.x - mx) + expf(c4.y - mx)) + (expf(c4.z - mx) + expf(c4.w - mx));
+                const float s3 = (expf(d4.x - mx) + expf(d4.y - mx)) + (expf(d4.z - mx) + expf(d4.w - mx));
+                se += (s0 + s1) + (s2 + s3);
+            }
+        }
+        for (; v < V; v += kStride) {
             float x0, x1 = -INFINITY, x2 = -INFINITY, x3 = -INFINITY;
             if (v + 3 < V) {
                 const float4 x = *reinterpret_cast<const float4*>(lp + v);

@@ -56,13 +56,23 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <bool GELU>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UTHREADS2, 1)
 umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                             const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                             int M, int N, int K, const float* __restrict__ bias, float w_unscale, float* __restrict__ C,
                             __half* __restrict__ C_h1, __half* __restrict__ C_h2, int ldc, int n_fastest,
-                            int* __restrict__ overflow) {
+                            int* __restrict__ overflow, int full_items, int tail_s, float* __restrict__ part) {
     constexpr int BN = 256, KE = 64, NST = U2_STAGES;
     constexpr int kChunkBlocks = UKC16;
     extern __shared__ uint8_t smem_raw[];
@@ -80,7 +90,18 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
     const int pm_tiles = (m_tiles + 1) / 2;                     // pair-tiles along M (256 rows each)
     const int total = pm_tiles * n_tiles;
     const int num_k = K / KE;
-    const int num_chunks = (num_k + kChunkBlocks - 1) / kChunkBlocks;
+    // Work list: items [0, full_items) are whole pair-tiles (all of K); the pair-tiles that would form a
+    // mostly idle last wave are cut into tail_s K-slices each, so that wave costs 1/tail_s of a tile time:
+    // item full_items + j = slice j % tail_s of pair-tile full_items + j / tail_s, raw partial sums stored to
+    // part[(tile - full_items) * tail_s + slice][256][256] (umma_tail_finish_kernel adds the slices in order).
+    const int total_items = full_items + (total - full_items) * tail_s;
+    struct Item { int tile, kb0, nkb, slot; };
+    auto decode = [&](int item) {
+        Item w;
+        if (item < full_items) { w.tile = item; w.kb0 = 0; w.nkb = num_k; w.slot = -1; }
+        else { const int j = item - full_items; w.tile = full_items + j / tail_s; w.nkb = num_k / tail_s; w.kb0 = (j % tail_s) * w.nkb; w.slot = j; }
+        return w;
+    };
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -101,11 +122,12 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
         if (lane == 0) {
             const uint32_t lead_full0 = map_to_cta(full0, 0);   // full barriers live in the leader CTA
             uint32_t it = 0;
-            for (int item = pair; item < total; item += n_pairs) {
-                const int pm = n_fastest ? item / n_tiles : item % pm_tiles, n_tile = n_fastest ? item % n_tiles : item / pm_tiles;
+            for (int item = pair; item < total_items; item += n_pairs) {
+                const Item w = decode(item);
+                const int pm = n_fastest ? w.tile / n_tiles : w.tile % pm_tiles, n_tile = n_fastest ? w.tile % n_tiles : w.tile / pm_tiles;
                 const int row_a = (2 * pm + (int)rank) * UM;                 // this CTA's 128 rows of A
                 const int row_w = n_tile * BN + (int)rank * 128;             // this CTA's half of the W tile
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                for (int kb = w.kb0; kb < w.kb0 + w.nkb; ++kb, ++it) {
                     const int s = it % NST;
                     const uint32_t ph = (it / NST) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
@@ -124,14 +146,16 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
             // D=F32 (1<<4), A=B=F16, K-major both, N>>3 at bit 17, M>>4 at bit 24 with M = 256 for the pair
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
             uint32_t it = 0, ch = 0;
-            for (int item = pair; item < total; item += n_pairs) {
+            for (int item = pair; item < total_items; item += n_pairs) {
+                const int num_k_item = decode(item).nkb;
+                const int num_chunks = (num_k_item + kChunkBlocks - 1) / kChunkBlocks;
                 int kb = 0;
                 for (int c = 0; c < num_chunks; ++c, ++ch) {
                     const int buf = ch & 1;
                     mbar_wait(tempty0 + 8 * buf, ((ch >> 1) & 1) ^ 1);       // both CTAs' epilogues drained this buffer
                     tc_fence_after();
                     const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                    const int kend = (kb + kChunkBlocks < num_k) ? kb + kChunkBlocks : num_k;
+                    const int kend = (kb + kChunkBlocks < num_k_item) ? kb + kChunkBlocks : num_k_item;
                     for (int k0 = kb; kb < kend; ++kb, ++it) {
                         const int s = it % NST;
                         const uint32_t ph = (it / NST) & 1;
@@ -157,9 +181,8 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
         const int cg = (warp - 4) >> 2;
         const uint32_t lead_tempty0 = map_to_cta(tempty0, 0);
         uint32_t ch = 0;
-        for (int item = pair; item < total; item += n_pairs) {
-            const int pm = n_fastest ? item / n_tiles : item % pm_tiles, n_tile = n_fastest ? item % n_tiles : item / pm_tiles;
-            const int m_tile = 2 * pm + (int)rank;
+        for (int item = pair; item < total_items; item += n_pairs) {
+            const int num_chunks = ((item < full_items ? num_k : num_k / tail_s) + kChunkBlocks - 1) / kChunkBlocks;
             float acc[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) acc[j] = 0.f;
@@ -168,20 +191,28 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
                 mbar_wait(tfull0 + 8 * buf, (ch >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cg * 64 + h * 32), r);
+                for (int h = 0; h < 4; ++h) {                     // 16 columns at a time: 64 accumulators + 16 fresh values fit 96 registers
+                    uint32_t r[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cg * 64 + h * 16), r);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[h * 32 + j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 16; ++j) acc[h * 16 + j] += __uint_as_float(r[j]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(lead_tempty0 + 8 * buf);
             }
+            const Item w = decode(item);                      // (kept out of the chunk loop: register pressure)
+            const int pm = n_fastest ? w.tile / n_tiles : w.tile % pm_tiles, n_tile = n_fastest ? w.tile % n_tiles : w.tile / pm_tiles;
+            const int m_tile = 2 * pm + (int)rank;
             const int row0 = m_tile * UM + q * 32;
             const int nb = n_tile * BN + cg * 64;
             float* stg = stage_base + (warp - 4) * 512;
-            if (row0 < M && nb < N) {
+            if (w.slot >= 0) {
+                // K-slice of a tail tile: raw sums, lane = row, 64 consecutive floats per lane (L2-resident scratch)
+                float* dst = part + ((int64_t)w.slot * 256 + rank * 128 + q * 32 + lane) * 256 + cg * 64;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            } else if (row0 < M && nb < N) {
 #pragma unroll
                 for (int pass = 0; pass < 4; ++pass) {
 #pragma unroll
@@ -240,6 +271,39 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+// Finishes the K-sliced tail tiles of umma_gemm_f16x3_2cta_kernel: out = act((sum_s part[t][s]) * w_unscale + bias),
+// slices added in index order (deterministic).  One thread per 4 consecutive columns of a 256 x 256 pair-tile.
+template <bool GELU>
+__global__ void __launch_bounds__(256) umma_tail_finish_kernel(int M, int N, int ldc, int n_tiles, int pm_tiles, int n_fastest,
+                                                               int full_items, int tail_s, const float* __restrict__ part,
+                                                               const float* __restrict__ bias, float w_unscale, float* __restrict__ C,
+                                                               __half* __restrict__ C_h1, __half* __restrict__ C_h2, int* __restrict__ overflow) {
+    const int t = blockIdx.x >> 6;                                // tail tile; 64 blocks of 256 threads x float4 each
+    const int e = ((blockIdx.x & 63) << 8) + threadIdx.x;
+    const int lr = e >> 6, c4 = e & 63;
+    const int tile = full_items + t;
+    const int pm = n_fastest ? tile / n_tiles : tile % pm_tiles, n_tile = n_fastest ? tile % n_tiles : tile / pm_tiles;
+    const int row = pm * 256 + lr, n = n_tile * 256 + c4 * 4;
+    if (row >= M || n >= N) return;
+    const float* p = part + ((int64_t)t * tail_s * 256 + lr) * 256 + c4 * 4;
+    float4 a = *reinterpret_cast<const float4*>(p);
+    for (int sl = 1; sl < tail_s; ++sl) {
+        const float4 b = *reinterpret_cast<const float4*>(p + (int64_t)sl * 65536);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    const int64_t off = (int64_t)row * ldc + n;
+    int ov = 0;
+    for (int u = 0; u < 4; ++u) {
+        if (n + u >= N) continue;
+        float x = v[u] * w_unscale + (bias ? bias[n + u] : 0.f);
+        if (GELU) x = gelu_erf_u(x);
+        if (C) C[off + u] = x;
+        if (C_h1) { __half h1, h2; split_half(x, h1, h2, &ov); C_h1[off + u] = h1; C_h2[off + u] = h2; }
+    }
+    if (ov) atomicExch(overflow, 1);
 }
 
 }  // namespace sealb200
