@@ -379,12 +379,17 @@ template <int ROUNDS>
 __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel(int64_t R, int d, int heads, int cur_pos, int T,
                                                                const float* __restrict__ qkv, float* kc, float* vc,
                                                                const int32_t* __restrict__ anc,
-                                                               float* __restrict__ out, SplitOut so) {
+                                                               float* __restrict__ out, SplitOut so, int row_mul, int bcast) {
+    // row_mul / bcast: at the first decode step all beams of a query are the same row (same start token, same
+    // source), so the step runs on one row per query: compact row r stands for physical rows r*row_mul ..
+    // r*row_mul + bcast - 1, whose cache entries all receive this row's k / v (any of them may become the
+    // ancestor of a later beam).  Every other step: row_mul = bcast = 1.
     const int64_t r = blockIdx.x;
+    const int64_t pr = r * row_mul;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 3, i8 = (lane & 7) * 8;
     const int n_keys = cur_pos + 1;                            // <= 32
-    const int32_t* arow = anc + r * T;
+    const int32_t* arow = anc + pr * T;
     for (int h = warp; h < heads; h += blockDim.x >> 5) {
         const int col = h * kHeadDim + i8;
         const float* qp = qkv + r * 3 * d + col;
@@ -398,11 +403,13 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
             store_split4(so, idx, o0); store_split4(so, idx + 4, o1);
             // persist this position's k, v for the later steps
             const float* kcur = qp + d; const float* vcur = qp + 2 * d;
-            float* kd = kc + ((int64_t)cur_pos * R + r) * d + col; float* vd = vc + ((int64_t)cur_pos * R + r) * d + col;
-            *reinterpret_cast<float4*>(kd) = __ldg(reinterpret_cast<const float4*>(kcur));
-            *reinterpret_cast<float4*>(kd + 4) = __ldg(reinterpret_cast<const float4*>(kcur + 4));
-            *reinterpret_cast<float4*>(vd) = __ldg(reinterpret_cast<const float4*>(vcur));
-            *reinterpret_cast<float4*>(vd + 4) = __ldg(reinterpret_cast<const float4*>(vcur + 4));
+            const float4 k0 = __ldg(reinterpret_cast<const float4*>(kcur)), k1 = __ldg(reinterpret_cast<const float4*>(kcur + 4));
+            const float4 v0 = __ldg(reinterpret_cast<const float4*>(vcur)), v1 = __ldg(reinterpret_cast<const float4*>(vcur + 4));
+            for (int b2 = 0; b2 < bcast; ++b2) {
+                float* kd = kc + ((int64_t)cur_pos * R + pr + b2) * d + col; float* vd = vc + ((int64_t)cur_pos * R + pr + b2) * d + col;
+                *reinterpret_cast<float4*>(kd) = k0; *reinterpret_cast<float4*>(kd + 4) = k1;
+                *reinterpret_cast<float4*>(vd) = v0; *reinterpret_cast<float4*>(vd + 4) = v1;
+            }
         }
     }
 }

@@ -468,10 +468,17 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
 }
 
 // one decoder step for all R rows: token at position pos = cur_len-1 -> logits [R][ld]
+// `compact` (first step of a generate only): every beam of a query is the same row there (same start token, same
+// source), so the step runs on one row per query -- Q rows instead of Q*B -- and the select kernel reads that
+// row's logits for all of the query's beams (StepCfg::logits_shared); the k / v of position 0 are written to the
+// cache entries of all B beams.  1/T of the decoder + lm_head work disappears (~8 % of a 9-step generate).
 void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, const int32_t* anc, bool want_logits,
-                  cudaEvent_t ev_layers_done) {
+                  cudaEvent_t ev_layers_done, bool compact = false) {
     sealbart* m = cx.m;
-    const int d = D.d; const int64_t R = D.R; const int64_t Tk = D.Q * D.S;
+    const int d = D.d; const int64_t Rc = D.R; const int64_t Tk = D.Q * D.S;
+    if (compact && (cur_len != 1 || D.grp_start)) throw ApiError(SEALFM_EINVAL, "internal: compact step only at position 0 of a generate");
+    const int64_t R = compact ? D.Q : D.R;          // rows processed
+    const int row_mul = compact ? D.B : 1;
     const int pos = cur_len - 1;
     const int gm = m->cfg.gemm_mode;
     auto mk = [&](float* plain, Buf& bh, Buf& bl, bool keep_plain) {
@@ -489,33 +496,33 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     const Act cq{m->dcq.as<float>()};
     const Act ffn = mk(m->dffn.as<float>(), m->dffn_hi, m->dffn_lo, false);
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
-    embed_ln_kernel<<<(unsigned)((R + 3) / 4), 128, 0, cx.s>>>(R, d, tokens + pos, D.T, nullptr, pos, m->shared, scale,
+    embed_ln_kernel<<<(unsigned)((R + 3) / 4), 128, 0, cx.s>>>(R, d, tokens + pos, D.T * row_mul, nullptr, pos, m->shared, scale,
                                                                m->dec_pos, m->dec_ln_emb.g, m->dec_ln_emb.b, x.x, split_of(x, ovf));
     CUDA_CHECK(cudaGetLastError()); m->launches++;
     const int heads = m->cfg.heads;
     const int32_t* m32 = m->enc_mask.as<int32_t>();
     for (int l = 0; l < m->cfg.decoder_layers; ++l) {
         DecLayerW& L = m->dec[l];
-        float* kc = m->kc.as<float>() + (size_t)l * D.T * R * d;
-        float* vc = m->vc.as<float>() + (size_t)l * D.T * R * d;
+        float* kc = m->kc.as<float>() + (size_t)l * D.T * Rc * d;
+        float* vc = m->vc.as<float>() + (size_t)l * D.T * Rc * d;
         gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         if (pos + 1 <= 12)
-            dec_self_attn_kernel<3><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
-                                                                                      attn.x, split_of(attn, ovf));
+            dec_self_attn_kernel<3><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(Rc, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                                      attn.x, split_of(attn, ovf), row_mul, row_mul);
         else
-            dec_self_attn_kernel<8><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(R, d, heads, pos, D.T, qkv.x, kc, vc, anc,
-                                                                                      attn.x, split_of(attn, ovf));
+            dec_self_attn_kernel<8><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(Rc, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                                      attn.x, split_of(attn, ovf), row_mul, row_mul);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
         const int64_t groups = D.grp_start ? D.G : D.Q;
         if (D.S <= kXKeys)
-            cross_attn_small_kernel<<<dim3((unsigned)groups, heads), 128, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
+            cross_attn_small_kernel<<<dim3((unsigned)groups, heads), 128, 0, cx.s>>>(groups, d, heads, compact ? 1 : D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
                                                                             D.grp_query, D.grp_start, attn.x, split_of(attn, ovf));
         else
-            cross_attn_kernel<<<dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s>>>(groups, d, heads, D.B, (int)D.S, cq.x,
+            cross_attn_kernel<<<dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s>>>(groups, d, heads, compact ? 1 : D.B, (int)D.S, cq.x,
                                                                             m->ckv.as<float>() + (size_t)l * Tk * 2 * d, m32,
                                                                             D.grp_query, D.grp_start, attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
@@ -736,9 +743,12 @@ int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d,
             const int cur_len = step + 1;
             cudaEvent_t a = new_event(m), b = new_event(m), cc = new_event(m), dd = new_event(m);
             CUDA_CHECK(cudaEventRecord(a, cx.s));
-            decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b);
+            static const bool compact_first = [] { const char* e = std::getenv("SEALB200_COMPACT_FIRST"); return !e || std::atoi(e) != 0; }();
+            const bool compact = compact_first && cur_len == 1;
+            decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b, compact);
             CUDA_CHECK(cudaEventRecord(cc, cx.s));
             c.cur_len = cur_len;
+            c.logits_shared = compact ? 1 : 0;
             const int eff_len = cur_len - (p->forced_bos_token_id >= 0 ? 1 : 0);
             c.first_step_shared_mask = (!p->disable_fm_index && eff_len == 1) ? 1 : 0;
             c.expand_next = (cur_len + 1 < T) ? 1 : 0;

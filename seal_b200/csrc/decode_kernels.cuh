@@ -30,6 +30,7 @@ struct StepCfg {
     int32_t mask_words;                // words per bitmask row
     int32_t first_step_shared_mask;    // 1: every row uses occurring_mask (seal/beam_search.py:73-77)
     int32_t expand_next;               // 0 on the last step
+    int32_t logits_shared;             // 1 (first step): one logits row per QUERY, shared by its beams (identical rows)
     int64_t hyps_per_query;
     int32_t hyp_base;                  // index of this step's first hypothesis record
 };
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
 
     for (int b = 0; b < B; ++b) {
         const int64_t r = r0 + b;
-        const float* lp = st.logits + r * c.ld;
+        const float* lp = st.logits + (c.logits_shared ? qi : r) * c.ld;
         // Exact pruning: every candidate of this row scores <= beam_score (log-probs <= 0, forced tokens
         // add 0).  Once K candidates are held and the row's beam score is below the K-th best, nothing
         // in the row can enter the top-K and no fill-in will be needed -> skip the row entirely,
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         for (int flat = 0; have < K && flat < B * V; ++flat) {
             const int b = flat / V, v = flat - b * V;
             const int64_t r = r0 + b;
-            float p = (st.logits[r * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
+            float p = (st.logits[(c.logits_shared ? qi : r) * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
             p = apply_processors(c, v, p);
             const float s = p + st.beam_scores_in[r];
             // was it a finite constrained candidate (then it is already in the list)?
