@@ -745,10 +745,20 @@ int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d,
             CUDA_CHECK(cudaEventRecord(a, cx.s));
             static const bool compact_first = [] { const char* e = std::getenv("SEALB200_COMPACT_FIRST"); return !e || std::atoi(e) != 0; }();
             const bool compact = compact_first && cur_len == 1;
-            decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b, compact);
+            // Dead step: when ForcedEOSTokenLogitsProcessor fires (cur_len == max_length - 1, HF semantics restated
+            // in apply_processors) it overwrites EVERY processed score with a constant, so neither the recorded
+            // hypotheses nor the (already final) beams depend on the model output of this step -- the reference
+            // computes it and discards it.  Nothing later reads this position's k / v either.
+            static const bool skip_dead = [] { const char* e = std::getenv("SEALB200_SKIP_DEAD_STEP"); return !e || std::atoi(e) != 0; }();
+            const bool forced_all = p->forced_eos_token_id >= 0 && cur_len == p->max_length - 1 && cur_len + 1 == T &&
+                                    !(p->forced_bos_token_id >= 0 && cur_len == 1);
+            const bool dead = skip_dead && forced_all;
+            if (!dead) decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b, compact);
+            else CUDA_CHECK(cudaEventRecord(b, cx.s));
             CUDA_CHECK(cudaEventRecord(cc, cx.s));
             c.cur_len = cur_len;
-            c.logits_shared = compact ? 1 : 0;
+            c.logits_shared = (compact && !dead) ? 1 : 0;
+            c.logits_ignored = dead ? 1 : 0;
             const int eff_len = cur_len - (p->forced_bos_token_id >= 0 ? 1 : 0);
             c.first_step_shared_mask = (!p->disable_fm_index && eff_len == 1) ? 1 : 0;
             c.expand_next = (cur_len + 1 < T) ? 1 : 0;

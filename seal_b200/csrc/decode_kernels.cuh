@@ -31,6 +31,8 @@ struct StepCfg {
     int32_t first_step_shared_mask;    // 1: every row uses occurring_mask (seal/beam_search.py:73-77)
     int32_t expand_next;               // 0 on the last step
     int32_t logits_shared;             // 1 (first step): one logits row per QUERY, shared by its beams (identical rows)
+    int32_t logits_ignored;            // 1: a forcing processor overwrites every score of this step (apply_processors),
+                                       //    so the model was not run and `logits` must not be read
     int64_t hyps_per_query;
     int32_t hyp_base;                  // index of this step's first hypothesis record
 };
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         // ---- full-vocabulary log-softmax statistics (seal/beam_search.py:251), ONE streaming pass:
         // per-thread running (max, sum exp(x - max)), merged across the block.
         float mx = -INFINITY, se = 0.f;
+        if (c.logits_ignored) { mx = 0.f; se = 1.f; }           // log-softmax statistics are never used (uniform branch)
+        else {
         // four 16-byte loads in flight per thread, one running-max update per 16 values (the loop is bound by
         // load latency and instruction issue, not by HBM: profiles/r01_ncu_select_v2_raw.csv)
         constexpr int kStride = kSelThreads * 4;
@@ -211,6 +215,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             se = block_reduce_sum(scaled, S.red);
             mx = bm;
         }
+        }
         const float logsum = logf(se);
         // ---- which tokens does the index allow on this row (seal/beam_search.py:87-135) ----------
         const int32_t* trow = st.tokens_in + r * c.T;
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             return bits;
         };
         auto consider = [&](int v, bool guarded) {
-            float p = (lp[v] - mx) - logsum;
+            float p = c.logits_ignored ? 0.f : (lp[v] - mx) - logsum;
             p = apply_processors(c, v, p);
             const float s = p + bs;
             const int flat = b * V + v;
@@ -302,7 +307,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         for (int flat = 0; have < K && flat < B * V; ++flat) {
             const int b = flat / V, v = flat - b * V;
             const int64_t r = r0 + b;
-            float p = (st.logits[(c.logits_shared ? qi : r) * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
+            float p = c.logits_ignored ? 0.f : (st.logits[(c.logits_shared ? qi : r) * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
             p = apply_processors(c, v, p);
             const float s = p + st.beam_scores_in[r];
             // was it a finite constrained candidate (then it is already in the list)?
