@@ -251,7 +251,12 @@ def run_ours(args):
                                   f"{Q} queries/GPU (seed 4321+rank), beam {BEAM}, min=max_length {MAX_LEN}, BART-large "
                                   "random init seed 0, fp32", "queries_per_gpu": Q, "beam": BEAM, "decode_steps": MAX_LEN - 1,
                       "parallelism": f"query-sharded x{world}, index+weights replicated, one NCCL gather",
-                      "l2": "per-step working set (KV cache + logits > 10 GB) exceeds L2; no explicit flush"},
+                      "l2": "per-step working set (KV cache + logits > 10 GB) exceeds L2; no explicit flush",
+                      "exact_work_elision": "results identical to the full computation (parity tests): the first decode step runs on one "
+                                            "row per query (its beams are identical rows) [SEALB200_COMPACT_FIRST=%s]; the step whose scores "
+                                            "ForcedEOS overwrites entirely (the 9th) has no model forward [SEALB200_SKIP_DEAD_STEP=%s]; "
+                                            "all 9 select/record steps run" % (os.environ.get("SEALB200_COMPACT_FIRST", "1"),
+                                                                               os.environ.get("SEALB200_SKIP_DEAD_STEP", "1"))},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "roofline": roof, "rank_kernel": rank_kernel, "phases_us_last_step": phases,
            "cpu_baseline": cpu_baseline_sample(args) if world == 1 else None}   # rank 0 at N = 1 only
