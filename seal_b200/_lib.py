@@ -105,6 +105,10 @@ _DEC_SIGS = {
     "sealdec_debug_gemm": (i32, [i32, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_int32,
                                  C.POINTER(C.c_double)]),
     "sealdec_debug_gemm_trace": (i32, [i32, C.POINTER(C.c_int64)]),
+    "sealev_first_stage": (i32, [C.c_int64, vp, vp, vp, vp, C.c_int64, vp, vp, vp, i32, i32, C.c_double, C.c_double, C.c_int64, vp, vp]),
+    "sealev_score_docs": (i32, [C.c_int64, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, i32, i32, i32, i32,
+                                C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int64]),
+    "sealev_last_error": (C.c_char_p, []),
     "sealdec_last_launch_count": (C.c_int64, [vp]),
     "sealdec_profile_gemm": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "sealdec_last_phase_us": (i32, [vp, C.POINTER(C.c_double)]),

@@ -165,6 +165,13 @@ class FMIndex(_FMIndex):
             return []
         return [(t.astype(np.int64) - SHIFT).tolist() for t in self.extract_text_batch(b, e)]
 
+    def get_docs_arrays(self, doc_indices):
+        """get_docs without the list conversion: int64 arrays of token ids."""
+        b = [self.beginnings[d] for d in doc_indices]; e = [self.beginnings[d + 1] for d in doc_indices]
+        if not b:
+            return []
+        return [t.astype(np.int64) - SHIFT for t in self.extract_text_batch(b, e)]
+
     def prefix_allowed_tokens_fn(self):
         """fairseq/GENRE-style hook named by BASELINE.json:north_star:
         prefix_allowed_tokens_fn(batch_id, input_ids) -> List[int] (index.py:128-134 semantics)."""

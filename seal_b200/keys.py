@@ -155,8 +155,12 @@ class _Evidence:
     def unigram_table(self, unigram_scores, given, cutoff):                                 # :237-272
         p = self.p
         V = len(unigram_scores)
-        order = sorted(range(V), reverse=True, key=lambda t: unigram_scores[t])
-        kept = [t for t in order[:p["use_top_k_unigrams"]] if t not in given]
+        # sorted(range(V), reverse=True, key=score)[:k] (:240-241): a stable sort of the negated scores keeps the
+        # lower token id first among ties, like reverse=True on a stable sort does
+        us = np.asarray(unigram_scores, dtype=np.float64)
+        order = np.argsort(-us, kind="stable")[:p["use_top_k_unigrams"]].tolist()
+        kept = [t for t in order if t not in given]
+        unigram_scores = us.tolist() if not isinstance(unigram_scores, list) else unigram_scores
         self.need_ranges([(t,) for t in kept])               # only the kept ones can score above zero
         table = [0.0] * V
         for t in kept:
@@ -219,121 +223,123 @@ def aggregate_evidence(ngrams_and_scores, unigram_scores: Optional[List[float]] 
     spans = []
     for k in rare:
         lo, hi = ev.range_of[k]
-        spans.append((lo, min(hi, lo + max_occurrences_1)))
-    if spans:
-        rows = np.concatenate([np.arange(a, b, dtype=np.uint64) for a, b in spans]) if any(b > a for a, b in spans) \
-            else np.zeros(0, dtype=np.uint64)
-        pos, doc = index.locate_rows(rows) if len(rows) else (rows, rows.astype(np.int64))
-        pos, doc = pos.tolist(), doc.tolist()
+        spans.append((lo, max(lo, min(hi, lo + max_occurrences_1))))
+    if any(b > a for a, b in spans):
+        rows = np.concatenate([np.arange(a, b, dtype=np.uint64) for a, b in spans])
+        pos, doc = index.locate_rows(rows)
     else:
-        pos, doc = [], []
+        pos, doc = np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.int64)
+    sort_mode = 1 if sort_by_length else (2 if sort_by_freq else 0)
+    empty_count = int(counts[()])
 
-    covered = set()                                                                         # :316-351
-    stage1 = {}                                   # doc -> [sum, [(key, score)...], [best key, best score]]
-    at = 0
-    for (k, sc), (a, b) in zip(rare.items(), spans):
-        n = len(k)
-        rank_new = (n, sc) if sort_by_length else ((-counts[k], sc) if sort_by_freq else sc)
-        credited = set()
-        for j in range(at, at + max(b - a, 0)):
-            end, d = pos[j], doc[j]
-            e = stage1.get(d)
-            if e is None:
-                e = stage1[d] = [0.0, [], [[], 0.0]]
-            bk, bs = e[2]
-            rank_old = (len(bk), bs) if sort_by_length else ((-counts[tuple(bk)], bs) if sort_by_freq else bs)
-            if rank_new > rank_old:
-                e[2] = [k, sc]
-            fresh = covered.isdisjoint(range(end - n, end))
-            if fresh:
-                covered.update(range(end - n, end))
-            if (fresh or allow_overlaps) and d not in credited:
-                credited.add(d)
-                e[0] += sc
-                e[1].append((k, sc))
-        at += max(b - a, 0)
-
-    for e in stage1.values():                                                               # :353-365
-        seen, total = set(), 0.0
-        for j, (k, sc) in enumerate(e[1]):
-            types = set(k)
-            adj = ev.damp(types, sc, seen)
-            total += adj
-            e[1][j] = [k, adj]
-            seen |= types
-        e[0] = total
-
-    shortlist = sorted(stage1.items(), key=lambda kv: (1.0 - single_key) * (-kv[1][0]) + single_key * (-kv[1][2][1]))
-    shortlist = [d for d, _ in shortlist[:n_docs_complete_score]]                           # :367-368
+    # first stage (:316-368) in native code: coverage of token positions, one credit per (key, document), damping
+    # of repeated token types, shortlist of the n_docs_complete_score best documents
+    rk = _FlatKeys(list(rare.items()), counts)
+    span_off = np.zeros(len(spans) + 1, dtype=np.int64)
+    np.cumsum([b - a for a, b in spans], out=span_off[1:])
+    shortlist = np.zeros(max(len(pos), 1), dtype=np.int64); n_short = C.c_int64(0)
+    _evcheck(lib.sealev_first_stage(len(rk), rk.tok.ctypes.data, rk.off.ctypes.data, rk.score.ctypes.data, rk.count.ctypes.data,
+                                    empty_count, span_off.ctypes.data, np.ascontiguousarray(pos, dtype=np.uint64).ctypes.data,
+                                    np.ascontiguousarray(doc, dtype=np.int64).ctypes.data, sort_mode, int(bool(allow_overlaps)),
+                                    float(beta), float(single_key), int(n_docs_complete_score), shortlist.ctypes.data,
+                                    C.byref(n_short)))
+    shortlist = shortlist[:n_short.value].tolist()
 
     # -- batch 3: the shortlisted documents' tokens -----------------------------------------------
-    texts = index.get_docs(shortlist)
-    scored = {k: v for k, v in all_ngrams.items() if len(k) >= 1 and v > 0.0}               # :378-385
-    stems = {k[:n] for k in scored for n in range(1, len(k) + 1)}
-
+    fetch = getattr(index, "get_docs_arrays", None)
+    texts = fetch(shortlist) if fetch else [np.asarray(t, dtype=np.int64) for t in index.get_docs(shortlist)]
+    docs_arr = []
+    for t in texts:                                                                         # :389: [2] + doc[:-1]
+        a = np.empty(max(len(t), 1), dtype=np.int64)
+        a[0] = 2; a[1:] = t[:-1]
+        docs_arr.append(a)
+    docs_tok = [a.tolist() for a in docs_arr]
+    scored = [(k, v) for k, v in all_ngrams.items() if len(k) >= 1 and v > 0.0]             # trie contents, :378-385
+    sk = _FlatKeys(scored, counts)
+    doc_off = np.zeros(len(docs_tok) + 1, dtype=np.int64)
+    np.cumsum([len(t) for t in docs_tok], out=doc_off[1:])
+    flat = np.concatenate(docs_arr) if docs_arr else np.zeros(0, dtype=np.int64)
+    uni = np.ascontiguousarray(unigram_scores, dtype=np.float64) if unigram_scores is not None else None
+    n = len(docs_tok)
+    out_score = np.zeros(max(n, 1)); out_best = np.zeros(max(n, 1), dtype=np.int64); out_best_score = np.zeros(max(n, 1))
+    pick_off = np.zeros(n + 1, dtype=np.int64)
+    cap = int(doc_off[-1]) * 2 + 16                       # a document cannot pick more keys + unigram types than it has tokens
+    pick_key = np.zeros(cap, dtype=np.int64); pick_score = np.zeros(cap)
+    _evcheck(lib.sealev_score_docs(len(sk), sk.tok.ctypes.data, sk.off.ctypes.data, sk.score.ctypes.data, sk.count.ctypes.data,
+                                   empty_count, n, flat.ctypes.data, doc_off.ctypes.data,
+                                   uni.ctypes.data if uni is not None else None, len(uni) if uni is not None else 0, sort_mode,
+                                   int(bool(allow_overlaps)), int(bool(unigrams_ignore_free_places)),
+                                   int(bool(single_key_add_unigrams)), float(beta), float(single_key), out_score.ctypes.data,
+                                   out_best.ctypes.data, out_best_score.ctypes.data, pick_off.ctypes.data, pick_key.ctypes.data,
+                                   pick_score.ctypes.data, cap))
     results = {}
-    for d, text in zip(shortlist, texts):                                                   # :387-491
-        toks = [2] + text[:-1]
-        hits = _scan_keys(toks, scored, stems)
-        best = [[], 0.0]
-        queue = []
-        for k, (s, places) in hits.items():                                                 # :413-432
-            if sort_by_length:
-                ahead = (-len(k), -s) < (-len(best[0]), -best[1])
-            elif sort_by_freq:
-                ahead = (counts[k], -s) < (counts[tuple(best[0])], -best[1])
-            else:
-                ahead = -s < -best[1]
-            if ahead:
-                best = [k, s]
-            queue += [(-s, k, s, a, b) for a, b in places]
-        queue.sort()                              # the reference's heap is filled completely before it is drained
-        seen, picked, prev = set(), [], None
-        free = [True] * len(toks)
-        for _, k, s, a, b in queue:                                                         # :434-470
-            if prev == k:
-                adj = picked[-1][1]
-            else:
-                adj = ev.damp(k, s, seen)
-            if adj <= 0.0 or not (allow_overlaps or all(free[a:b])):
-                continue
-            if prev != k:
-                prev = k
-                seen.update(k)
-                picked.append((k, adj))
-            free[a:b] = [False] * (b - a)
-        if unigrams_ignore_free_places:
-            free = [True] * len(toks)
-        total = sum(s for _, s in picked)
-        uni = 0.0
-        if unigram_scores is not None:                                                      # :479-486 (all-zero otherwise)
-            for t in _Counter(t for t, f in zip(toks, free) if f):
-                s = unigram_scores[t]
-                if s > 0.0:
-                    s = ev.damp((t,), s, seen)
-                    if s != 0.0:
-                        uni += s
-                        picked.append(((t,), s))
-        lone = best[1] + (uni if single_key_add_unigrams else 0.0)
-        total += uni
-        results[d] = [(1.0 - single_key) * total + single_key * lone, picked, None, toks, best]
+    pk, ps, po = pick_key.tolist(), pick_score.tolist(), pick_off.tolist()
+    for i, d in enumerate(shortlist):
+        picked = [((scored[k][0] if k >= 0 else (-1 - k,)), s) for k, s in zip(pk[po[i]:po[i + 1]], ps[po[i]:po[i + 1]])]
+        b = int(out_best[i])
+        best = [scored[b][0], float(out_best_score[i])] if b >= 0 else [[], 0.0]
+        results[d] = [float(out_score[i]), picked, None, docs_tok[i], best]
     return dict(sorted(results.items(), key=lambda kv: -kv[1][0])), all_ngrams              # :496-497
 
 
-def _scan_keys(toks, scored, stems):
+class _FlatKeys:
+    """(key tuple, score) pairs flattened for the native calls (include/sealev.h)."""
+
+    def __init__(self, items, counts):
+        self.off = np.zeros(len(items) + 1, dtype=np.int64)
+        np.cumsum([len(k) for k, _ in items], out=self.off[1:])
+        self.tok = np.fromiter((t for k, _ in items for t in k), dtype=np.int64, count=int(self.off[-1])) if items else np.zeros(0, dtype=np.int64)
+        if len(self.tok) == 0:
+            self.tok = np.zeros(1, dtype=np.int64)
+        self.score = np.array([s for _, s in items], dtype=np.float64) if items else np.zeros(1)
+        self.count = np.array([counts[tuple(k)] for k, _ in items], dtype=np.int64) if items else np.zeros(1, dtype=np.int64)
+        self.n = len(items)
+
+    def __len__(self):
+        return self.n
+
+
+def _evcheck(code):
+    if code != 0:
+        from ._lib import SealB200Error
+        raise SealB200Error(code, lib.sealev_last_error().decode(errors="replace"))
+
+
+_END = -1                                         # trie slot holding (key, score) of a complete key
+
+
+def _build_trie(scored):
+    root = {}
+    for k, sc in scored.items():
+        node = root
+        for t in k:
+            node = node.setdefault(t, {})
+        node[_END] = (k, sc)
+    return root
+
+
+def _scan_keys(toks, root):
     """All occurrences of the scored keys in one document -> {key: [score, [(start, end)...]]}, keys in the
     order the reference's open-match list discovers them (it is popped from its END at every position,
     keys.py:400-409, so the visiting order of the live partial matches flips from one token to the next;
-    only the order in which equal-scored keys are met depends on it)."""
+    only the order in which equal-scored keys are met depends on it).  Partial matches are (start, trie node)
+    pairs, so a position costs one dict lookup per live match instead of a tuple slice and two set probes."""
     hits = {}
     live = []
-    for i in range(len(toks)):
+    for i, t in enumerate(toks):
         keep = []
-        for a in reversed(live + [i]):
-            k = tuple(toks[a:i + 1])
-            if k in stems:
-                keep.append(a)
-                if k in scored:
-                    hits.setdefault(k, [scored[k], []])[1].append((a, i + 1))
+        node = root.get(t)                        # the match starting here is visited first
+        if node is not None:
+            keep.append((i, node))
+            end = node.get(_END)
+            if end is not None:
+                hits.setdefault(end[0], [end[1], []])[1].append((i, i + 1))
+        for a, node in reversed(live):
+            node = node.get(t)
+            if node is not None:
+                keep.append((a, node))
+                end = node.get(_END)
+                if end is not None:
+                    hits.setdefault(end[0], [end[1], []])[1].append((a, i + 1))
         live = keep
     return hits

@@ -20,7 +20,7 @@ def test_abi_library_loads_and_exports_every_declared_symbol():
     for hdr in sorted(os.listdir(os.path.join(ROOT, "include"))):
         text = open(os.path.join(ROOT, "include", hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-        names = set(re.findall(r"\b(seal(?:fm|dec|bart)_[a-z0-9_]+)\s*\(", text))
+        names = set(re.findall(r"\b(seal(?:fm|dec|bart|ev)_[a-z0-9_]+)\s*\(", text))
         assert names, hdr
         for n in sorted(names):
             assert hasattr(_lib.lib, n), f"{n} declared in include/{hdr} but not exported"
