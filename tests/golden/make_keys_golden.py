@@ -153,5 +153,58 @@ def main():
     print("wrote keys_golden.json", os.path.getsize(os.path.join(HERE, "keys_golden.json")), "bytes")
 
 
+def fuzz(n_cases):
+    """Randomised cross-check (nothing stored): the reference function vs the oracle restatement on small corpora with
+    many score ties, repeated keys and every flag combination -- the orders the fixtures cannot pin exhaustively."""
+    import itertools
+    from oracle.keys_oracle import aggregate_evidence_oracle
+    ref = load_reference_keys()
+    rng = np.random.default_rng(2024)
+    flags = ["sort_by_length", "sort_by_freq", "allow_overlaps", "use_fm_index_frequency", "add_best_unigrams_to_ngrams",
+             "single_key_add_unigrams", "unigrams_ignore_free_places"]
+    bad = 0
+    for case in range(n_cases):
+        vocab = int(rng.integers(30, 200))
+        docs = make_corpus(n_docs=int(rng.integers(5, 60)), doc_len=int(rng.integers(6, 20)), n_phrases=int(rng.integers(5, 40)),
+                           seed=int(rng.integers(0, 1 << 30)), vocab=vocab)
+        index = OracleIndex([list(map(int, d)) for d in docs], backend="ref")
+        levels = -np.round(rng.exponential(2.0, size=4), 1) - 0.1               # few distinct scores -> ties everywhere
+        keys = []
+        for _ in range(int(rng.integers(1, 25))):
+            d = int(rng.integers(0, docs.shape[0])); L = int(rng.integers(1, 5)); a = int(rng.integers(0, docs.shape[1] - L))
+            k = [int(t) for t in docs[d, a:a + L]]
+            if rng.random() < 0.15:
+                k[-1] = int(rng.integers(4, vocab))
+            keys.append((k, float(levels[int(rng.integers(0, len(levels)))])))
+        uni = None
+        if rng.random() < 0.7:
+            z = np.round(rng.standard_normal(vocab), 1)                          # ties among unigram scores too
+            uni = (z - np.log(np.exp(z).sum())).tolist()
+        kw = {f: bool(rng.random() < 0.4) for f in flags}
+        kw["use_fm_index_frequency"] = not kw["use_fm_index_frequency"] if rng.random() < 0.5 else True
+        kw.update(max_occurrences_1=int(rng.choice([1, 3, 50, 1500])), n_docs_complete_score=int(rng.choice([1, 5, 500])),
+                  single_key=float(rng.choice([0.0, 0.3, 1.0])), beta=float(rng.choice([0.0, 0.8, 1.0])),
+                  alpha=float(rng.choice([1.0, 2.0])), length_penalty=float(rng.choice([0.0, 0.2])),
+                  use_top_k_unigrams=int(rng.choice([3, 1000])), max_occurrences_2=int(rng.choice([10, 10_000_000])))
+        try:
+            exp = dump_result(*ref.aggregate_evidence([(list(k), s) for k, s in keys], unigram_scores=uni, index=index, **kw))
+        except Exception as e:                                                   # the oracle must fail the same way
+            try:
+                aggregate_evidence_oracle([(list(k), s) for k, s in keys], unigram_scores=uni, index=index, **kw)
+                print("case", case, "reference raised", type(e).__name__, "but the oracle did not"); bad += 1
+            except Exception as e2:
+                if type(e2) is not type(e):
+                    print("case", case, "different exceptions", type(e).__name__, type(e2).__name__); bad += 1
+            continue
+        got = dump_result(*aggregate_evidence_oracle([(list(k), s) for k, s in keys], unigram_scores=uni, index=index, **kw))
+        if got != exp:
+            bad += 1
+            print("case", case, "MISMATCH", kw)
+    print(f"fuzz: {n_cases} cases, {bad} mismatches")
+    return bad
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--fuzz":
+        sys.exit(1 if fuzz(int(sys.argv[2])) else 0)
     main()

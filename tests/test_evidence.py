@@ -184,3 +184,49 @@ def test_product_rescore_and_unigram_match_reference_outputs():
         assert np.array_equal(np.isfinite(lp[:, :64]), fin)
         assert np.abs(lp[:, :64][fin] - head[fin]).max() < 2e-5
         assert np.abs(lp.max(-1) - np.array(c["row_max"])).max() < 2e-5
+
+
+def test_product_host_logic_fuzz_against_oracle():
+    """Tie-heavy random cases (few distinct scores, repeated keys, every flag): the product function -- batched index
+    calls answered by the oracle-backed double, order-defining loops in native code -- must return exactly what the
+    oracle restatement returns (which tests/golden/make_keys_golden.py --fuzz checks against the reference function)."""
+    from oracle.fm_oracle import OracleIndex
+    from oracle.keys_oracle import aggregate_evidence_oracle
+    from seal_b200.keys import aggregate_evidence
+    rng = np.random.default_rng(77)
+    flags = ["sort_by_length", "sort_by_freq", "allow_overlaps", "add_best_unigrams_to_ngrams", "single_key_add_unigrams",
+             "unigrams_ignore_free_places"]
+    checked = 0
+    for case in range(80):
+        vocab = int(rng.integers(30, 200))
+        docs = make_corpus(n_docs=int(rng.integers(5, 60)), doc_len=int(rng.integers(6, 20)), n_phrases=int(rng.integers(5, 40)),
+                           seed=int(rng.integers(0, 1 << 30)), vocab=vocab)
+        ora = OracleIndex([list(map(int, d)) for d in docs])
+        levels = -np.round(rng.exponential(2.0, size=4), 1) - 0.1
+        keys = []
+        for _ in range(int(rng.integers(1, 25))):
+            d = int(rng.integers(0, docs.shape[0])); L = int(rng.integers(1, 5)); a = int(rng.integers(0, docs.shape[1] - L))
+            k = [int(t) for t in docs[d, a:a + L]]
+            if rng.random() < 0.15:
+                k[-1] = int(rng.integers(4, vocab))
+            keys.append((k, float(levels[int(rng.integers(0, len(levels)))])))
+        uni = None
+        if rng.random() < 0.7:
+            z = np.round(rng.standard_normal(vocab), 1)
+            uni = (z - np.log(np.exp(z).sum())).tolist()
+        kw = {f: bool(rng.random() < 0.4) for f in flags}
+        kw.update(use_fm_index_frequency=bool(rng.random() < 0.75), max_occurrences_1=int(rng.choice([1, 3, 50, 1500])),
+                  n_docs_complete_score=int(rng.choice([1, 5, 500])), single_key=float(rng.choice([0.0, 0.3, 1.0])),
+                  beta=float(rng.choice([0.0, 0.8, 1.0])), alpha=float(rng.choice([1.0, 2.0])),
+                  length_penalty=float(rng.choice([0.0, 0.2])), use_top_k_unigrams=int(rng.choice([3, 1000])),
+                  max_occurrences_2=int(rng.choice([10, 10_000_000])))
+        try:
+            exp = flatten(*aggregate_evidence_oracle([(list(k), s) for k, s in keys], unigram_scores=uni, index=ora, **kw))
+        except Exception:
+            with pytest.raises(Exception):
+                aggregate_evidence([(list(k), s) for k, s in keys], unigram_scores=uni, index=_BatchedOracleIndex(ora), **kw)
+            continue
+        got = flatten(*aggregate_evidence([(list(k), s) for k, s in keys], unigram_scores=uni, index=_BatchedOracleIndex(ora), **kw))
+        assert got == exp, (case, kw)
+        checked += 1
+    assert checked > 50

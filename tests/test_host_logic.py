@@ -154,3 +154,17 @@ def test_device_primitives_on_host_match_goldens(hostcheck, name):
         L.hc_extract(h, int(b), int(e), o.ctypes.data)
         assert np.array_equal(o[: int(e) - int(b)], ex[int(eo[i]):int(eo[i + 1])])
     L.hc_free(h)
+
+
+def test_gpu_index_builder_reports_missing_device():
+    """sealfm_build_gpu must fail loudly (SEALFM_ENODEVICE), never fall back to the host builder, without a GPU."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    from seal_b200 import _lib
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a CUDA device is present")
+    a = np.array([5, 6, 7], dtype=np.uint64); out = C.c_void_p()
+    assert _lib.lib.sealfm_build_gpu(a.ctypes.data, 3, 0, C.byref(out)) == -4
+    assert out.value is None
