@@ -193,5 +193,53 @@ def main():
     print("wrote decode_golden.json", os.path.getsize(os.path.join(HERE, "decode_golden.json")), "bytes")
 
 
+def fuzz(n_cases):
+    """Randomised cross-check (nothing stored): the reference's fm_index_generate vs the oracle restatement on random
+    parameter combinations -- same hypotheses in the same order, |dscore| < 1e-5, or the same exception type."""
+    ref = load_reference_beam_search()
+    docs = make_corpus(**CORPUS)
+    ora = OracleIndex([d.tolist() for d in docs], backend="ref")
+    model = make_bart(**MODEL)
+    adapter = Bart413Adapter(model)
+    rng = np.random.default_rng(31337)
+    bad = raised = 0
+    for case in range(n_cases):
+        max_length = int(rng.integers(3, 11))
+        kw = dict(num_beams=int(rng.integers(1, 9)), max_length=max_length, min_length=int(rng.integers(0, max_length + 1)),
+                  length_penalty=float(rng.choice([0.0, 0.5, 1.0])))
+        if rng.random() < 0.3: kw["always_allow_eos"] = True
+        if rng.random() < 0.3: kw["stop_at_count"] = int(rng.choice([1, 2, 5]))
+        if rng.random() < 0.25:
+            d = int(rng.integers(0, docs.shape[0])); a = int(rng.integers(0, docs.shape[1] - 3))
+            kw["force_decoding_from"] = [int(t) for t in docs[d, a:a + int(rng.integers(1, 3))]]
+        if rng.random() < 0.2: kw["forced_bos_token_id"] = 0
+        if rng.random() < 0.15: kw["disable_fm_index"] = True
+        if rng.random() < 0.2: kw["eos_token_id"] = int(rng.integers(4, CORPUS["vocab"]))
+        ids, am = make_inputs(rng, Q=int(rng.integers(1, 4)), S=int(rng.integers(4, 13)), vocab=CORPUS["vocab"])
+        try:
+            a = ref.fm_index_generate(adapter, ora, ids, am, keep_history=True, **kw)
+        except Exception as e:
+            raised += 1
+            try:
+                fm_index_generate_oracle(model, ora, ids, am, **kw)
+                print("case", case, kw, "reference raised", type(e).__name__, e, "but the oracle did not"); bad += 1
+            except Exception as e2:
+                if type(e2) is not type(e):
+                    print("case", case, kw, "different exceptions", type(e).__name__, type(e2).__name__); bad += 1
+            continue
+        b = fm_index_generate_oracle(model, ora, ids, am, **kw)
+        ok = len(a) == len(b)
+        for qa, qb in zip(a, b):
+            ok = ok and [tuple(t) for _, t in qa] == [tuple(t) for _, t, _ in qb]
+            ok = ok and all(abs(x[0] - y[0]) < 1e-5 for x, y in zip(qa, qb))
+        if not ok:
+            bad += 1
+            print("case", case, "MISMATCH", kw)
+    print(f"fuzz: {n_cases} cases ({raised} where both raise), {bad} mismatches")
+    return bad
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--fuzz":
+        sys.exit(1 if fuzz(int(sys.argv[2])) else 0)
     main()
