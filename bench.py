@@ -255,8 +255,9 @@ def run_ours(args):
                       "exact_work_elision": "results identical to the full computation (parity tests): the first decode step runs on one "
                                             "row per query (its beams are identical rows) [SEALB200_COMPACT_FIRST=%s]; the step whose scores "
                                             "ForcedEOS overwrites entirely (the 9th) has no model forward [SEALB200_SKIP_DEAD_STEP=%s]; "
-                                            "all 9 select/record steps run" % (os.environ.get("SEALB200_COMPACT_FIRST", "1"),
-                                                                               os.environ.get("SEALB200_SKIP_DEAD_STEP", "1"))},
+                                            "all 9 select/record steps run; the encoder runs on the real (unpadded) source tokens [SEALB200_PACK_ENCODER=%s]"
+                                            % (os.environ.get("SEALB200_COMPACT_FIRST", "1"), os.environ.get("SEALB200_SKIP_DEAD_STEP", "1"),
+                                               os.environ.get("SEALB200_PACK_ENCODER", "1"))},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
            "roofline": roof, "rank_kernel": rank_kernel, "phases_us_last_step": phases,
            "cpu_baseline": cpu_baseline_sample(args) if world == 1 else None}   # rank 0 at N = 1 only

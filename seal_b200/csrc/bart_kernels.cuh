@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
 struct GroupAddr {
     const float* q; int64_t q_stride;        // query row r of the group: q + r * q_stride (+ head offset)
     const float* k; const float* v; int64_t kv_stride;   // key s: k + s * kv_stride (+ head offset)
-    const int32_t* mask;                     // [n_keys], 0 = padded key
+    const int32_t* mask;                     // [n_keys], 0 = padded key; nullptr = every key valid (packed sources)
 };
 
 template <int NW, int MAXP>
@@ -458,7 +458,7 @@ __device__ __forceinline__ void grouped_attention(const GroupAddr& g, int rows, 
                 Kt[4 * i4 + 0][s] = kk.x; Kt[4 * i4 + 1][s] = kk.y; Kt[4 * i4 + 2][s] = kk.z; Kt[4 * i4 + 3][s] = kk.w;
                 *reinterpret_cast<float4*>(&Vs[s][4 * i4]) = vv;
             }
-            if (threadIdx.x < 32) valid_s[threadIdx.x] = (s0 + threadIdx.x < n_keys) && g.mask[s0 + threadIdx.x] != 0;
+            if (threadIdx.x < 32) valid_s[threadIdx.x] = (s0 + threadIdx.x < n_keys) && (!g.mask || g.mask[s0 + threadIdx.x] != 0);
             __syncthreads();
             const bool ok = valid_s[lane] != 0;
             const int cnt = n_keys - s0 < 32 ? n_keys - s0 : 32;
@@ -516,14 +516,17 @@ __global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G,
                                                          const int32_t* __restrict__ src_mask,
                                                          const int32_t* __restrict__ grp_query,
                                                          const int32_t* __restrict__ grp_start, float* __restrict__ out,
-                                                         SplitOut so) {
+                                                         SplitOut so, const int32_t* __restrict__ src_off) {
+    // src_off (packed sources): query qi's encoder states are rows src_off[qi] .. src_off[qi+1] of ckv, all valid
     const int64_t gi = blockIdx.x;
     const int h = blockIdx.y;
     const int64_t qi = grp_query ? grp_query[gi] : gi;
     const int64_t row0 = grp_start ? grp_start[gi] : gi * beams;
     const int rows = grp_start ? grp_start[gi + 1] - grp_start[gi] : beams;
-    GroupAddr g{q + row0 * d, d, ckv + qi * S * 2 * d, ckv + qi * S * 2 * d + d, 2 * d, src_mask + qi * S};
-    grouped_attention<kGAttnWarps, kGAttnPasses>(g, rows, S, h * kHeadDim, row0 * d, d, out, so);
+    const int64_t k0 = src_off ? src_off[qi] : qi * S;
+    const int Sq = src_off ? src_off[qi + 1] - src_off[qi] : S;
+    GroupAddr g{q + row0 * d, d, ckv + k0 * 2 * d, ckv + k0 * 2 * d + d, 2 * d, src_off ? nullptr : src_mask + qi * S};
+    grouped_attention<kGAttnWarps, kGAttnPasses>(g, rows, Sq, h * kHeadDim, row0 * d, d, out, so);
 }
 
 // Cross attention for sources of at most 32 positions (every decode shape of the benchmark: S <= 28): one CTA of
@@ -534,12 +537,12 @@ __global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G,
 // sweep spends two shared-memory reads per FMA (profiles/r01_SUMMARY.md).  Same ragged-group arguments as
 // cross_attn_kernel.
 constexpr int kXKeys = 32, kXRows = 16, kXPad = kHeadDim + 4;
-__global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d, int heads, int beams, int S,
+__global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d, int heads, int beams, int S_pad,
                                                                const float* __restrict__ q, const float* __restrict__ ckv,
                                                                const int32_t* __restrict__ src_mask,
                                                                const int32_t* __restrict__ grp_query,
                                                                const int32_t* __restrict__ grp_start, float* __restrict__ out,
-                                                               SplitOut so) {
+                                                               SplitOut so, const int32_t* __restrict__ src_off) {
     __shared__ __align__(16) float Ks[kXKeys][kXPad];
     __shared__ __align__(16) float Vs[kXKeys][kHeadDim];
     __shared__ __align__(16) float Qs[kXRows][kHeadDim];
@@ -550,7 +553,9 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
     const int64_t qi = grp_query ? grp_query[gi] : gi;
     const int64_t row0 = grp_start ? grp_start[gi] : gi * beams;
     const int rows = grp_start ? grp_start[gi + 1] - grp_start[gi] : beams;
-    const float* kbase = ckv + qi * S * 2 * d + head_off;
+    // src_off (packed sources): this query's states are rows src_off[qi] .. src_off[qi+1], all valid
+    const int S = src_off ? src_off[qi + 1] - src_off[qi] : S_pad;
+    const float* kbase = ckv + (src_off ? (int64_t)src_off[qi] : qi * S_pad) * 2 * d + head_off;
     const float* vbase = kbase + d;
     const int tid = threadIdx.x, lane = tid & 31, rg = tid >> 5;
     for (int e = tid; e < kXKeys * (kHeadDim / 4); e += 128) {
@@ -563,7 +568,7 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
         *reinterpret_cast<float4*>(&Ks[sidx][4 * i4]) = kk;
         *reinterpret_cast<float4*>(&Vs[sidx][4 * i4]) = vv;        // rows >= S stay zero: their weight is 0, never 0 * garbage
     }
-    const bool key_ok = lane < S && src_mask[qi * S + (lane < S ? lane : 0)] != 0;
+    const bool key_ok = lane < S && (src_off || src_mask[qi * S_pad + lane] != 0);
     for (int rbase = 0; rbase < rows; rbase += kXRows) {
         __syncthreads();                                           // K/V staged; previous block's Qs / Ps consumed
         for (int e = tid; e < kXRows * (kHeadDim / 4); e += 128) {
@@ -629,12 +634,15 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
 __global__ void __launch_bounds__(kGAttnWarps * 32) enc_self_attn_kernel(int64_t Q, int d, int heads, int S,
                                                             const float* __restrict__ qkv,
                                                             const int32_t* __restrict__ src_mask,
-                                                            float* __restrict__ out, SplitOut so) {
+                                                            float* __restrict__ out, SplitOut so,
+                                                            const int32_t* __restrict__ src_off) {
     const int64_t qi = blockIdx.x;
     const int h = blockIdx.y;
-    const float* base = qkv + qi * S * 3 * d;
-    GroupAddr g{base, 3 * d, base + d, base + 2 * d, 3 * d, src_mask + qi * S};
-    grouped_attention<kGAttnWarps, kGAttnPasses>(g, S, S, h * kHeadDim, qi * S * d, d, out, so);
+    const int64_t r0 = src_off ? src_off[qi] : qi * S;       // packed: only the real tokens of each query are rows
+    const int n = src_off ? src_off[qi + 1] - src_off[qi] : S;
+    const float* base = qkv + r0 * 3 * d;
+    GroupAddr g{base, 3 * d, base + d, base + 2 * d, 3 * d, src_off ? nullptr : src_mask + qi * S};
+    grouped_attention<kGAttnWarps, kGAttnPasses>(g, n, n, h * kHeadDim, r0 * d, d, out, so);
 }
 
 }  // namespace sealb200
