@@ -231,18 +231,35 @@ def generate_records(model, index, input_ids, attention_mask, min_length=3, max_
 
 
 def records_to_output(rec, length_penalty):
-    """beam_search.py:555: [(score * len**lp, tokens) for every recorded hyp with score > -inf]."""
-    out = []
+    """beam_search.py:555: [(score * len**lp, tokens) for every recorded hyp with score > -inf].
+    The arithmetic is vectorised (float64, like the reference's Python floats; len**lp comes from a table filled
+    with Python's own pow so that every bit matches); only the final tuples are built in a Python loop."""
     scores, lens, toks = rec["scores"], rec["lens"], rec["tokens"]
-    for q in range(scores.shape[0]):
-        s = scores[q].astype(np.float64).tolist(); l = lens[q].tolist(); t = toks[q].tolist()
+    Q = scores.shape[0]
+    if scores.size == 0:
+        return [[] for _ in range(Q)]
+    pen_table = np.array([float(n) ** length_penalty if n > 0 else 1.0 for n in range(int(lens.max()) + 1)], dtype=np.float64)
+    pen = pen_table[lens]
+    hyp = scores.astype(np.float64) / pen                             # BeamHypothesesWithMemory.add, :752-755
+    final = hyp * pen
+    valid = hyp > float("-inf")
+    # one flat list of the kept tokens (prefixes of the kept hypotheses), sliced per hypothesis
+    n_kept = np.where(valid, lens, 0)
+    keep_tok = valid[:, :, None] & (np.arange(toks.shape[2])[None, None, :] < lens[:, :, None])
+    flat = toks[keep_tok].tolist()
+    ends = np.cumsum(n_kept.reshape(-1)[valid.reshape(-1)]).tolist()
+    fs = final[valid].tolist()
+    per_query = valid.sum(axis=1).tolist()
+    out = []
+    i = 0; start = 0
+    for cnt in per_query:
         row = []
-        for i in range(len(s)):
-            n = l[i]
-            sc = s[i] / (n ** length_penalty)                     # BeamHypothesesWithMemory.add, :752-755
-            if sc > float("-inf"):
-                row.append((sc * n ** length_penalty, t[i][:n]))
+        for j in range(i, i + cnt):
+            e = ends[j]
+            row.append((fs[j], flat[start:e]))
+            start = e
         out.append(row)
+        i += cnt
     return out
 
 
