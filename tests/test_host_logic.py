@@ -168,3 +168,26 @@ def test_gpu_index_builder_reports_missing_device():
     a = np.array([5, 6, 7], dtype=np.uint64); out = C.c_void_p()
     assert _lib.lib.sealfm_build_gpu(a.ctypes.data, 3, 0, C.byref(out)) == -4
     assert out.value is None
+
+
+def test_records_to_output_matches_the_reference_formula():
+    """beam_search.py:555 / :752-755 restated literally vs the vectorised product conversion (every bit)."""
+    import numpy as np
+    from seal_b200.beam_search import records_to_output
+    rng = np.random.default_rng(5)
+    Q, H, T = 7, 40, 9
+    rec = {"scores": (rng.standard_normal((Q, H)) * 5 - 20).astype(np.float32), "lens": rng.integers(1, T + 1, size=(Q, H)).astype(np.int32),
+           "tokens": rng.integers(0, 50000, size=(Q, H, T)).astype(np.int32)}
+    rec["scores"][rng.random((Q, H)) < 0.4] = -np.inf
+    rec["scores"][2, :] = -np.inf                                    # a query whose hypotheses are all masked
+    for lp in (0.0, 0.5, 1.0, 0.37):
+        exp = []
+        for q in range(Q):
+            row = []
+            for i in range(H):
+                n = int(rec["lens"][q, i])
+                sc = float(rec["scores"][q, i]) / (n ** lp)
+                if sc > float("-inf"):
+                    row.append((sc * n ** lp, rec["tokens"][q, i, :n].tolist()))
+            exp.append(row)
+        assert records_to_output(rec, lp) == exp
