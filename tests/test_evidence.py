@@ -230,3 +230,28 @@ def test_product_host_logic_fuzz_against_oracle():
         assert got == exp, (case, kw)
         checked += 1
     assert checked > 50
+
+
+def test_product_edge_cases_against_oracle():
+    """Empty key lists, keys that do not occur, no unigram scores, an empty shortlist, and the IndexError the reference
+    raises for use_fm_index_frequency=False without keys: same value or same exception type as the restatement."""
+    from oracle.fm_oracle import OracleIndex
+    from oracle.keys_oracle import aggregate_evidence_oracle
+    from seal_b200.keys import aggregate_evidence
+    docs = make_corpus(n_docs=30, doc_len=12, n_phrases=20, seed=3, vocab=80)
+    ora = OracleIndex([list(map(int, d)) for d in docs])
+    uni = (np.zeros(80) - np.log(80.0)).tolist()
+    cases = [([], uni, {}), ([], None, {}), ([([79, 78, 77], -1.0)], uni, {}),
+             ([([int(docs[0, 0]), int(docs[0, 1])], -0.5)], None, {}),
+             ([([int(docs[0, 0])], -0.5)], uni, dict(n_docs_complete_score=0)),
+             ([], uni, dict(use_fm_index_frequency=False))]
+    for keys, u, kw in cases:
+        try:
+            exp, err = flatten(*aggregate_evidence_oracle(list(keys), unigram_scores=u, index=ora, **kw)), None
+        except Exception as e:
+            exp, err = None, type(e)
+        if err is not None:
+            with pytest.raises(err):
+                aggregate_evidence(list(keys), unigram_scores=u, index=_BatchedOracleIndex(ora), **kw)
+        else:
+            assert flatten(*aggregate_evidence(list(keys), unigram_scores=u, index=_BatchedOracleIndex(ora), **kw)) == exp
