@@ -58,9 +58,13 @@ int sealfm_build_from_file(const char* path, int width_bytes, sealfm_t** out);
  * Reads either an sdsl-lite 2.1.0 `csa_wt_int<>` stream (the published SEAL .fmi files) or this
  * library's native container (written by sealfm_save); auto-detected. */
 int sealfm_load(const char* path, sealfm_t** out);
-/* FMIndex::save(path)                                fm_index.cpp:186-189
- * Writes the native container (magic "SEALB2FM"); sealfm_load reads it back. */
+/* Writes this library's flat native container (magic "SEALB2FM"); sealfm_load reads it back.
+ * (The drop-in FMIndex.save uses sealfm_save_sdsl below.) */
 int sealfm_save(const sealfm_t* h, const char* path);
+/* FMIndex::save(path) in the REFERENCE'S OWN FORMAT: the byte stream sdsl::store_to_file(csa_wt_int<>) writes
+ * (fm_index.cpp:186-189, sdsl/csa_wt.hpp:374-384), including the rank / select tables the reference's loader
+ * expects -- an index built here loads in the unmodified reference's load_FMIndex. */
+int sealfm_save_sdsl(const sealfm_t* h, const char* path);
 void sealfm_free(sealfm_t* h);
 
 uint64_t sealfm_size(const sealfm_t* h);       /* FMIndex::size() = n+1   fm_index.cpp:50-52 */

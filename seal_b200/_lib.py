@@ -38,6 +38,7 @@ _FM_SIGS = {
     "sealfm_abi_version": (i32, []),
     "sealfm_build": (i32, [vp, u64, C.POINTER(vp)]),
     "sealfm_build_gpu": (i32, [vp, u64, i32, C.POINTER(vp)]),
+    "sealfm_save_sdsl": (i32, [vp, cp]),
     "sealfm_build_from_file": (i32, [cp, i32, C.POINTER(vp)]),
     "sealfm_load": (i32, [cp, C.POINTER(vp)]),
     "sealfm_save": (i32, [vp, cp]),

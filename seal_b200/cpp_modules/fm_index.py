@@ -165,8 +165,11 @@ class FMIndex:
                                       out.ctypes.data, len(out)))
         return out[: int(offs[1])].tolist()
 
-    def save(self, path):                                         # fm_index.cpp:186-189
-        check(lib.sealfm_save(self._handle(), os.fsencode(path)))
+    def save(self, path, native=False):                           # fm_index.cpp:186-189
+        """Writes the reference's own file format (sdsl csa_wt_int<> stream, byte-identical to what the reference's
+        FMIndex::save writes for the same text, so the file loads in the unmodified reference); native=True writes
+        this library's flat container instead.  load_FMIndex reads both."""
+        check((lib.sealfm_save if native else lib.sealfm_save_sdsl)(self._handle(), os.fsencode(path)))
 
     # -- batched extensions (not in the reference; same arithmetic, one launch) --------------------
     def backward_search_step_batch(self, symbols, lows, highs):

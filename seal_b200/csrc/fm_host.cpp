@@ -286,4 +286,209 @@ void save_index_native(const HostIndex& o, const std::string& path) {
     w(o.isa_samples.data(), nisa * 8);
 }
 
+// ------------------------------------------------------------------------------------------------
+// sdsl-compatible writer: the byte stream sdsl::store_to_file(csa_wt_int<>) produces for this index
+// (SURVEY.md Appendix A), so that an index built here -- on the GPU in tens of milliseconds -- loads in
+// the unmodified reference (load_FMIndex, fm_index.cpp:191-199).  Everything the reader above skips has to
+// be constructed: the rank_support_v blocks (sdsl/rank_support_v.hpp:67-106), the select_support_mcl
+// tables of the tree and of the alphabet's sd_vector (sdsl/select_support_mcl.hpp:209-345, both of its
+// construction paths -- they differ in how the last, partial superblock is stored) and the sd_vector
+// itself (sdsl/sd_vector.hpp:192-228).  tests/test_host_logic.py compares the files byte for byte with
+// the reference's own FMIndex::save where oracle/_ref is available.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct Writer {
+    FilePtr f; std::string path;
+    explicit Writer(const std::string& p) : f(fopen(p.c_str(), "wb")), path(p) {
+        if (!f) throw std::runtime_error("cannot open for writing: " + p);
+    }
+    void bytes(const void* d, size_t n) { if (n && fwrite(d, 1, n, f.get()) != n) throw std::runtime_error("short write: " + path); }
+    void u64(uint64_t v) { bytes(&v, 8); }
+    void u32(uint32_t v) { bytes(&v, 4); }
+    void u8(uint8_t v) { bytes(&v, 1); }
+};
+
+// sdsl int_vector<0> under construction: n entries of `width` bits
+struct Packed {
+    uint64_t n = 0; uint8_t width = 64; std::vector<uint64_t> w;
+    Packed() = default;
+    Packed(uint64_t count, uint8_t wd) : n(count), width(wd), w((count * wd + 63) / 64 + 1, 0) {}
+    bool empty() const { return n == 0; }
+    void set(uint64_t i, uint64_t v) {
+        if (width < 64) v &= (1ULL << width) - 1;                   // int_vector truncates
+        const uint64_t p = i * width, k = p >> 6, o = p & 63;
+        w[k] |= v << o;
+        if (o + width > 64) w[k + 1] |= v >> (64 - o);
+    }
+    void write(Writer& out, bool with_width_byte) const {
+        const uint64_t bits = n * width;
+        out.u64(bits);
+        if (with_width_byte) out.u8(width);
+        out.bytes(w.data(), ((bits + 63) >> 6) * 8);
+    }
+};
+
+struct BitView {                                                     // a bit_vector: `size` bits in 64-bit words
+    const uint64_t* w; uint64_t size;
+    uint64_t capacity() const { return ((size + 63) >> 6) << 6; }
+    bool bit(uint64_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+};
+
+inline int nth_set_bit(uint64_t x, uint64_t i) {                     // position of the i-th (1-based) set bit
+    for (uint64_t k = 1; k < i; ++k) x &= x - 1;
+    return __builtin_ctzll(x);
+}
+
+// select_support_mcl<b,1> over `v`, serialised (sdsl/select_support_mcl.hpp:425-463)
+void write_mcl(Writer& out, const BitView& v, int b) {
+    constexpr uint64_t SB = 4096;
+    auto is_arg = [&](uint64_t i) { return v.bit(i) == (b != 0); };
+    uint64_t arg_cnt = 0;
+    for (uint64_t i = 0; i < (v.size >> 6); ++i) arg_cnt += __builtin_popcountll(b ? v.w[i] : ~v.w[i]);
+    for (uint64_t i = (v.size >> 6) << 6; i < v.size; ++i) arg_cnt += is_arg(i);
+    out.u64(arg_cnt);
+    if (!arg_cnt) return;
+    const uint64_t logn = hi_bit(v.capacity()) + 1, logn4 = logn * logn * logn * logn;
+    const uint64_t sb = (arg_cnt + SB - 1) / SB;
+    Packed super(sb, (uint8_t)logn);
+    std::vector<Packed> mini(sb), lng(sb);
+    bool any_long = false;
+    std::vector<uint64_t> pos(SB);
+    if (v.size < 100000) {                                           // init_slow (:209-258)
+        uint64_t cnt = 0, sbi = 0;
+        for (uint64_t i = 0; i < v.size; ++i) {
+            if (!is_arg(i)) continue;
+            pos[cnt % SB] = i;
+            ++cnt;
+            if (cnt % SB == 0 || cnt == arg_cnt) {
+                const uint64_t last = (cnt - 1) % SB;
+                super.set(sbi, pos[0]);
+                const uint64_t diff = pos[last] - pos[0];
+                if (diff > logn4) {
+                    any_long = true;
+                    lng[sbi] = Packed(SB, (uint8_t)(hi_bit(pos[last]) + 1));
+                    for (uint64_t j = 0; j <= last; ++j) lng[sbi].set(j, pos[j]);
+                } else {
+                    mini[sbi] = Packed(64, (uint8_t)(hi_bit(diff) + 1));
+                    for (uint64_t j = 0; j <= last; j += 64) mini[sbi].set(j / 64, pos[j] - pos[0]);
+                }
+                ++sbi;
+            }
+        }
+    } else {                                                         // init_fast (:261-345): word-wise; only every 64th
+        uint64_t last_k64 = 1, last_k64_sum = 1, sbi = 0;            // argument position is kept while scanning
+        uint64_t cnt_old = 0, cnt_new = 0;
+        const uint64_t words = v.capacity() >> 6;
+        for (uint64_t wi = 0; wi < words; ++wi) {
+            const uint64_t word = b ? v.w[wi] : ~v.w[wi];
+            cnt_new += __builtin_popcountll(word);
+            if (cnt_new >= last_k64_sum) {
+                pos[last_k64 - 1] = wi * 64 + nth_set_bit(word, last_k64_sum - cnt_old);
+                last_k64 += 64; last_k64_sum += 64;
+                if (last_k64 == SB + 1) {
+                    super.set(sbi, pos[0]);
+                    uint64_t last_pos = pos[last_k64 - 65];
+                    for (uint64_t ii = pos[last_k64 - 65] + 1, j = last_k64 - 65; ii < v.size && j < SB; ++ii)
+                        if (is_arg(ii)) { last_pos = ii; ++j; }
+                    const uint64_t diff = last_pos - pos[0];
+                    if (diff > logn4) {
+                        any_long = true;
+                        lng[sbi] = Packed(SB, (uint8_t)(hi_bit(last_pos) + 1));
+                        for (uint64_t j = pos[0], k = 0; k < SB && j <= last_pos; ++j) if (is_arg(j)) lng[sbi].set(k++, j);
+                    } else {
+                        mini[sbi] = Packed(64, (uint8_t)(hi_bit(diff) + 1));
+                        for (uint64_t j = 0; j < SB; j += 64) mini[sbi].set(j / 64, pos[j] - pos[0]);
+                    }
+                    ++sbi;
+                    last_k64 = 1;
+                }
+            }
+            cnt_old = cnt_new;
+        }
+        if (last_k64 > 1) {                                          // the remainder is always stored as a long block
+            any_long = true;
+            lng[sbi] = Packed(SB, (uint8_t)(hi_bit(v.size - 1) + 1));
+            for (uint64_t i = pos[0], k = 0; i < v.size; ++i) if (is_arg(i)) lng[sbi].set(k++, i);
+            ++sbi;
+        }
+    }
+    super.write(out, true);
+    Packed mol;                                                      // bit i = superblock i is a mini block (:441-446)
+    if (any_long) { mol = Packed(sb, 1); for (uint64_t i = 0; i < sb; ++i) if (!mini[i].empty()) mol.set(i, 1); }
+    else { mol.n = 0; mol.width = 1; mol.w.assign(1, 0); }
+    mol.write(out, false);
+    for (uint64_t i = 0; i < sb; ++i) {
+        const bool use_long = any_long && mini[i].empty();
+        (use_long ? lng[i] : mini[i]).write(out, true);
+    }
+}
+
+}  // namespace
+
+void save_index_sdsl(const HostIndex& o, const std::string& path) {
+    Writer out(path);
+    const uint64_t m = o.size, L = o.max_level, tree_bits = m * L;
+    // ---- wt_int (sdsl/wt_int.hpp:693-705) ----
+    out.u64(m); out.u64(o.sigma);
+    out.u64(tree_bits); out.bytes(o.tree.data(), ((tree_bits + 63) >> 6) * 8);
+    {   // rank_support_v<1,1> (:67-106): per 512 bits [absolute count][seven 9-bit in-block counts]
+        const uint64_t cap = ((tree_bits + 63) >> 6) << 6, W = cap >> 6;
+        std::vector<uint64_t> bb(((cap >> 9) + 1) << 1, 0);
+        uint64_t sum = __builtin_popcountll(o.tree[0]), second = 0, j = 0, i = 1;
+        for (; i < W; ++i) {
+            if (!(i & 7)) { j += 2; bb[j - 1] = second; bb[j] = bb[j - 2] + sum; second = sum = 0; }
+            else second |= sum << (63 - 9 * (i & 7));
+            sum += __builtin_popcountll(o.tree[i]);
+        }
+        if (i & 7) { second |= sum << (63 - 9 * (i & 7)); bb[j + 1] = second; }
+        else { j += 2; bb[j - 1] = second; bb[j] = bb[j - 2] + sum; bb[j + 1] = 0; }
+        out.u64(bb.size() * 64); out.bytes(bb.data(), bb.size() * 8);
+    }
+    const BitView tree{o.tree.data(), tree_bits};
+    write_mcl(out, tree, 1);
+    write_mcl(out, tree, 0);
+    out.u32((uint32_t)L);
+    // ---- SA / ISA samples (sdsl/csa_sampling_strategy.hpp:85-99, :626-641): width hi(n)+1 ----
+    const uint8_t wn = (uint8_t)(hi_bit(m) + 1);
+    Packed sa(o.sa_samples.size(), wn), isa(o.isa_samples.size(), wn);
+    for (uint64_t i = 0; i < o.sa_samples.size(); ++i) sa.set(i, o.sa_samples[i]);
+    for (uint64_t i = 0; i < o.isa_samples.size(); ++i) isa.set(i, o.isa_samples[i]);
+    sa.write(out, true); isa.write(out, true);
+    // ---- int_alphabet (sdsl/csa_alphabet_strategy.hpp:494-534, :582-594) ----
+    bool continuous = true;
+    for (uint64_t c = 0; c < o.sigma; ++c) continuous = continuous && o.alphabet[c] == c;
+    if (continuous) {                                                // default-constructed sd_vector + supports
+        out.u64(0); out.u8(0);
+        Packed().write(out, true);                                   // m_low: empty int_vector<0>, width 64
+        out.u64(0);                                                  // m_high: empty bit_vector
+        out.u64(0); out.u64(0);                                      // the two select supports: no arguments
+    } else {                                                         // sd_vector over the "symbol present" bitmap (sd_vector.hpp:192-228)
+        const uint64_t n = o.alphabet.back() + 1, ones = o.sigma;
+        uint8_t logm = (uint8_t)(hi_bit(ones) + 1); const uint8_t logn = (uint8_t)(hi_bit(n) + 1);
+        if (logm == logn) --logm;
+        const uint8_t wl = logn - logm;
+        Packed low(ones, wl);
+        const uint64_t high_bits = ones + (1ULL << logm);
+        std::vector<uint64_t> high((high_bits + 63) / 64 + 1, 0);
+        uint64_t last_high = 0, highpos = 0;
+        for (uint64_t k = 0; k < ones; ++k) {
+            const uint64_t p = o.alphabet[k], cur_high = p >> wl;
+            highpos += cur_high - last_high; last_high = cur_high;
+            low.set(k, p);
+            high[highpos >> 6] |= 1ULL << (highpos & 63); ++highpos;
+        }
+        out.u64(n); out.u8(wl);
+        low.write(out, true);
+        out.u64(high_bits); out.bytes(high.data(), ((high_bits + 63) >> 6) * 8);
+        const BitView hv{high.data(), high_bits};
+        write_mcl(out, hv, 1);
+        write_mcl(out, hv, 0);
+    }
+    Packed C(o.sigma + 1, wn);
+    for (uint64_t i = 0; i <= o.sigma; ++i) C.set(i, o.C[i]);
+    C.write(out, true);
+    out.u64(o.sigma);
+}
+
 }  // namespace sealb200

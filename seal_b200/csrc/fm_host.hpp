@@ -29,5 +29,7 @@ void build_index_from_file(const std::string& path, int width_bytes, HostIndex& 
 void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex& out);
 void load_index(const std::string& path, HostIndex& out);        // sdsl .fmi or native, auto-detect
 void save_index_native(const HostIndex& idx, const std::string& path);
+// The byte stream sdsl::store_to_file(csa_wt_int<>) writes for this index: loads in the unmodified reference.
+void save_index_sdsl(const HostIndex& idx, const std::string& path);
 
 }  // namespace sealb200

@@ -345,6 +345,13 @@ int sealfm_save(const sealfm_t* h, const char* path) {
         catch (const std::runtime_error& e) { throw ApiError(SEALFM_EIO, e.what()); }
     });
 }
+int sealfm_save_sdsl(const sealfm_t* h, const char* path) {
+    return guarded([&] {
+        if (!h || !path) throw ApiError(SEALFM_EINVAL, "null argument");
+        try { save_index_sdsl(h->host, path); }
+        catch (const std::runtime_error& e) { throw ApiError(SEALFM_EIO, e.what()); }
+    });
+}
 void sealfm_free(sealfm_t* h) {
     if (!h) return;
     release_device(h);
