@@ -376,40 +376,46 @@ void write_mcl(Writer& out, const BitView& v, int b) {
                 ++sbi;
             }
         }
-    } else {                                                         // init_fast (:261-345): word-wise; only every 64th
-        uint64_t last_k64 = 1, last_k64_sum = 1, sbi = 0;            // argument position is kept while scanning
-        uint64_t cnt_old = 0, cnt_new = 0;
+    } else {
+        // Word-wise construction (the path sdsl takes from 100 000 bits on, :261-345).  Only the position of every
+        // 64th argument of the current superblock is recorded while scanning (`marks`); a superblock is closed as
+        // soon as its 4033rd argument (mark 63) has been seen, by walking on to its last argument.  What is left
+        // after the last closed superblock is always stored as a long block of width hi(size-1)+1.
+        uint64_t mark = 0;                 // marks recorded in the open superblock
+        uint64_t want = 1;                 // rank (1-based, over the whole vector) of the next argument to mark
+        uint64_t seen_before = 0, seen = 0, sbi = 0;
+        std::vector<uint64_t>& marks = pos;                          // marks[64 * k] = position of argument 64 k of the block
         const uint64_t words = v.capacity() >> 6;
         for (uint64_t wi = 0; wi < words; ++wi) {
             const uint64_t word = b ? v.w[wi] : ~v.w[wi];
-            cnt_new += __builtin_popcountll(word);
-            if (cnt_new >= last_k64_sum) {
-                pos[last_k64 - 1] = wi * 64 + nth_set_bit(word, last_k64_sum - cnt_old);
-                last_k64 += 64; last_k64_sum += 64;
-                if (last_k64 == SB + 1) {
-                    super.set(sbi, pos[0]);
-                    uint64_t last_pos = pos[last_k64 - 65];
-                    for (uint64_t ii = pos[last_k64 - 65] + 1, j = last_k64 - 65; ii < v.size && j < SB; ++ii)
-                        if (is_arg(ii)) { last_pos = ii; ++j; }
-                    const uint64_t diff = last_pos - pos[0];
-                    if (diff > logn4) {
+            seen += __builtin_popcountll(word);
+            if (seen >= want) {
+                marks[mark * 64] = wi * 64 + nth_set_bit(word, want - seen_before);
+                ++mark; want += 64;
+                if (mark == 64) {
+                    const uint64_t first = marks[0];
+                    uint64_t last = marks[63 * 64];
+                    for (uint64_t i = last + 1, have = 63 * 64; i < v.size && have < SB; ++i)
+                        if (is_arg(i)) { last = i; ++have; }
+                    super.set(sbi, first);
+                    if (last - first > logn4) {
                         any_long = true;
-                        lng[sbi] = Packed(SB, (uint8_t)(hi_bit(last_pos) + 1));
-                        for (uint64_t j = pos[0], k = 0; k < SB && j <= last_pos; ++j) if (is_arg(j)) lng[sbi].set(k++, j);
+                        lng[sbi] = Packed(SB, (uint8_t)(hi_bit(last) + 1));
+                        for (uint64_t i = first, k = 0; k < SB && i <= last; ++i) if (is_arg(i)) lng[sbi].set(k++, i);
                     } else {
-                        mini[sbi] = Packed(64, (uint8_t)(hi_bit(diff) + 1));
-                        for (uint64_t j = 0; j < SB; j += 64) mini[sbi].set(j / 64, pos[j] - pos[0]);
+                        mini[sbi] = Packed(64, (uint8_t)(hi_bit(last - first) + 1));
+                        for (uint64_t k = 0; k < 64; ++k) mini[sbi].set(k, marks[64 * k] - first);
                     }
                     ++sbi;
-                    last_k64 = 1;
+                    mark = 0;
                 }
             }
-            cnt_old = cnt_new;
+            seen_before = seen;
         }
-        if (last_k64 > 1) {                                          // the remainder is always stored as a long block
+        if (mark > 0) {
             any_long = true;
             lng[sbi] = Packed(SB, (uint8_t)(hi_bit(v.size - 1) + 1));
-            for (uint64_t i = pos[0], k = 0; i < v.size; ++i) if (is_arg(i)) lng[sbi].set(k++, i);
+            for (uint64_t i = marks[0], k = 0; i < v.size; ++i) if (is_arg(i)) lng[sbi].set(k++, i);
             ++sbi;
         }
     }
