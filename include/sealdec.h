@@ -108,20 +108,50 @@ int64_t sealdec_hyps_per_query(const sealdec_params_t* p);
  *   out_lo/out_hi uint64 [Q][H]      SA range [lo,hi) of the hypothesis' tokens[1:] (0,0 if invalid
  *                                    or FM index disabled); may be NULL
  * H = sealdec_hyps_per_query(p).  Returns SEALFM_EINVAL("beam") if some query had fewer than
- * num_beams non-EOS candidates (the reference raises ValueError, :687-690). */
+ * num_beams non-EOS candidates (the reference raises ValueError, :687-690).  If an activation leaves the fp16
+ * range of the default GEMM mode the pass is repeated with the 3xTF32 kernels (sealbart_get_stat "overflow_fallbacks"). */
 int sealdec_generate(sealbart_t* model, const sealfm_t* fm, const uint32_t* occurring_mask_host,
                      const sealdec_params_t* p, const int64_t* input_ids, const int64_t* attention_mask,
                      int64_t Q, int64_t S, float* out_scores, int32_t* out_len, int32_t* out_tokens,
                      uint8_t* out_valid, uint64_t* out_lo, uint64_t* out_hi);
 
-/* Same, inputs and outputs already resident on the model's device; asynchronous on `stream`
- * except for workspace (re)allocation.  *_d pointers are device pointers. */
+/* Same, inputs and outputs already resident on the model's device; asynchronous on `stream` except for
+ * workspace (re)allocation and -- without a source-token count, see sealdec_generate_dx -- one 16-byte read-back
+ * of the real source-token count.  *_d pointers are device pointers.
+ * error_flag_d: int32[4] on the device, zeroed by the call and raised by its kernels:
+ *   [0] some query had fewer than num_beams non-EOS candidates   (the reference raises ValueError, :687-690)
+ *   [1] an activation left the fp16 range of the 3xFP16 GEMM modes (|x| > 65504; operands were saturated): the
+ *       results are NOT to be used -- re-run after sealbart_set_option(model, "gemm_mode", 2) (3xTF32, fp32 range).
+ *       sealdec_generate (host buffers) does that by itself.
+ *   [2] src_tokens_hint did not match the attention mask
+ *   [3] reserved */
 int sealdec_generate_d(sealbart_t* model, const sealfm_t* fm, const uint32_t* occurring_mask_d,
                        const sealdec_params_t* p, const int64_t* input_ids_d,
                        const int64_t* attention_mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
                        float* out_scores_d, int32_t* out_len_d, int32_t* out_tokens_d,
                        uint8_t* out_valid_d, uint64_t* out_lo_d, uint64_t* out_hi_d,
                        int32_t* error_flag_d);
+/* sealdec_generate_d plus what the caller knows about the sources:
+ *   src_tokens_hint >= 1  the number of non-zero attention_mask entries, masks right-padded (the only kind SEAL
+ *                         builds): the encoder runs on the real tokens only and the call never touches the host;
+ *                         a wrong count raises error_flag_d[2];
+ *                   -1    unknown (sealdec_generate_d): one 16-byte device->host read to learn it;
+ *                   -2    compute the padded positions too (no host access either).
+ * On a non-default stream, batches of at most 4096 rows (queries x beams) are replayed from a CUDA graph of the
+ * whole call from the third call with the same shapes, parameters and buffer addresses on (a generate of 20
+ * queries is ~1 900 short kernels: launch-bound); sealbart_set_option(model, "cuda_graph", 0 / 1 / -1) forces it
+ * off / on / back to automatic. */
+int sealdec_generate_dx(sealbart_t* model, const sealfm_t* fm, const uint32_t* occurring_mask_d,
+                        const sealdec_params_t* p, const int64_t* input_ids_d,
+                        const int64_t* attention_mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
+                        float* out_scores_d, int32_t* out_len_d, int32_t* out_tokens_d,
+                        uint8_t* out_valid_d, uint64_t* out_lo_d, uint64_t* out_hi_d,
+                        int32_t* error_flag_d, int64_t src_tokens_hint);
+/* Options: "cuda_graph" (-1 auto, 0 off, 1 on), "gemm_mode" (switch between the 3xFP16 modes 3/4/5 and 2 = 3xTF32;
+ * the TF32 operand copies are made on first use).  Stats: "last_used_graph", "overflow_fallbacks", "gemm_mode",
+ * "cached_graphs" (-1 for an unknown name). */
+int     sealbart_set_option(sealbart_t* model, const char* name, int64_t value);
+int64_t sealbart_get_stat(const sealbart_t* model, const char* name);
 
 /* ---- teacher-forced scoring: SURVEY.md section 8(f) rank 1 ------------------------------------------
  * The decoder pass behind rescore_keys (seal/keys.py:64-141) and compute_unigram_scores (:145-176).

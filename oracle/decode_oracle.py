@@ -260,6 +260,37 @@ class HFBartStepper:
         return out.logits[:, -1, :].float().cpu()
 
 
+class HFBartCachedStepper:
+    """Same contract as HFBartStepper, but with the decoder KV cache the reference actually runs with
+    (`use_cache=True`, seal/beam_search.py:483; `_reorder_cache` after every step, :331-332): each call feeds only the
+    newest token and `reorder(beam_idx)` permutes the cache.  This is the honest CPU / eager-GPU baseline -- the
+    re-forwarding stepper does O(t^2) decoder work the reference does not do.  Checked against HFBartStepper in
+    tests/test_oracle.py (same hypotheses, |dscore| < 1e-5)."""
+
+    def __init__(self, model, input_ids, attention_mask, num_beams):
+        self.model = model
+        with torch.inference_mode():
+            enc = model.get_encoder()(input_ids=input_ids, attention_mask=attention_mask)
+        self.enc = enc.last_hidden_state.repeat_interleave(num_beams, dim=0)
+        self.mask = attention_mask.repeat_interleave(num_beams, dim=0)
+        self.cache = None
+
+    def __call__(self, decoder_input_ids):
+        from transformers.modeling_outputs import BaseModelOutput
+        with torch.inference_mode():
+            dec = decoder_input_ids.to(self.enc.device)
+            if self.cache is not None:
+                dec = dec[:, -1:]
+            out = self.model(encoder_outputs=BaseModelOutput(last_hidden_state=self.enc), attention_mask=self.mask,
+                             decoder_input_ids=dec, past_key_values=self.cache, use_cache=True)
+            self.cache = out.past_key_values
+        return out.logits[:, -1, :].float().cpu()
+
+    def reorder(self, beam_idx):
+        with torch.inference_mode():
+            self.cache.reorder_cache(beam_idx.to(self.enc.device))
+
+
 def make_bart(seed=0, device="cpu", layers=None, vocab=None, d_model=None):
     """BartConfig() defaults == facebook/bart-large; seeded random init; the three
     -inf bias entries SEAL sets at load time (seal/retrieval.py:584-588)."""
@@ -287,10 +318,12 @@ def make_bart(seed=0, device="cpu", layers=None, vocab=None, d_model=None):
 def fm_index_generate_oracle(model, index, input_ids, attention_mask, min_length=3, max_length=25,
                              length_penalty=1.0, num_beams=3, eos_token_id=None, force_decoding_from=None,
                              always_allow_eos=False, disable_fm_index=False, stop_at_count=0,
-                             processors=("min_length", "forced_bos", "forced_eos", "inf_nan"), trace=None, **kw):
-    """seal/beam_search.py:391-557 (keep_history=True path) on an HF BART model."""
+                             processors=("min_length", "forced_bos", "forced_eos", "inf_nan"), trace=None,
+                             use_cache=False, **kw):
+    """seal/beam_search.py:391-557 (keep_history=True path) on an HF BART model.  use_cache=True drives the decoder
+    with its KV cache like the reference does (baseline timing); the default re-forwards the prefix (simplest exact form)."""
     cfg = model.config
-    stepper = HFBartStepper(model, input_ids, attention_mask, num_beams)
+    stepper = (HFBartCachedStepper if use_cache else HFBartStepper)(model, input_ids, attention_mask, num_beams)
     forced_bos = kw.pop("forced_bos_token_id", cfg.forced_bos_token_id)           # :415-418
     return constrained_beam_search_oracle(
         stepper, input_ids.shape[0], index, num_beams, min_length, max_length, length_penalty,
@@ -298,4 +331,5 @@ def fm_index_generate_oracle(model, index, input_ids, attention_mask, min_length
         pad_token_id=cfg.pad_token_id, decoder_start_token_id=cfg.decoder_start_token_id,
         model_eos_token_id=cfg.eos_token_id, forced_eos_token_id=cfg.forced_eos_token_id,
         forced_bos_token_id=forced_bos, force_decoding_from=force_decoding_from, stop_at_count=stop_at_count,
-        always_allow_eos=always_allow_eos, disable_fm_index=disable_fm_index, processors=processors, trace=trace)
+        always_allow_eos=always_allow_eos, disable_fm_index=disable_fm_index, processors=processors, trace=trace,
+        reorder=stepper.reorder if use_cache else None)

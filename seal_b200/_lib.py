@@ -100,6 +100,10 @@ _DEC_SIGS = {
     "sealdec_generate": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]),
     "sealdec_generate_d": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp,
                                  vp, vp, vp]),
+    "sealdec_generate_dx": (i32, [vp, vp, vp, C.POINTER(DecParams), vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp,
+                                  vp, vp, vp, C.c_int64]),
+    "sealbart_set_option": (i32, [vp, cp, C.c_int64]),
+    "sealbart_get_stat": (C.c_int64, [vp, cp]),
     "sealdec_teacher_forced": (i32, [vp, vp, vp, C.c_int64, C.c_int64, vp, vp, C.c_int64, C.c_int64, C.c_float, vp,
                                      C.c_int64, vp]),
     "sealdec_debug_step_logits": (i32, [vp, vp, vp, C.c_int64, C.c_int64, C.c_int32, vp, C.c_int64, vp]),

@@ -230,6 +230,127 @@ def generate_records(model, index, input_ids, attention_mask, min_length=3, max_
     return {"scores": scores, "lens": lens, "tokens": toks, "valid": valid, "lo": lo, "hi": hi}
 
 
+class DeviceRecords:
+    """The hypothesis records of one generate call in ONE device buffer (sharding.RecordLayout): the decode
+    kernels write into it, `sharding.gather_buffers` moves it (NCCL, device to device), `.host()` reads it."""
+
+    def __init__(self, layout, device):
+        torch = _torch()
+        self.layout = layout
+        self.buf = torch.zeros(layout.nbytes, dtype=torch.uint8, device=device)
+        self._base = self.buf.data_ptr()
+
+    def ptr(self, name):
+        return self._base + self.layout.offsets[name][0]
+
+    @property
+    def err_ptr(self):
+        return self._base + self.layout.err_offset
+
+    def set_filled(self, n):
+        torch = _torch()
+        self.buf[:8] = torch.from_numpy(np.asarray([n], dtype=np.int64).view(np.uint8)).to(self.buf.device)
+
+    def host(self):
+        """Blocking read-back: dict of numpy arrays (first dim = the queries filled) + 'errors'."""
+        from .sharding import merge_gathered
+        return merge_gathered([self.buf], self.layout)
+
+
+def _side_stream(device):
+    """One non-default stream per device for the asynchronous entry points (CUDA graphs cannot be captured on the
+    legacy default stream, which is what torch.cuda.current_stream() is unless the caller changed it)."""
+    torch = _torch()
+    cache = _side_stream.__dict__.setdefault("cache", {})
+    key = torch.device(device).index if not isinstance(device, int) else device
+    if key not in cache:
+        cache[key] = torch.cuda.Stream(device=key)
+    return cache[key]
+
+
+def generate_records_device(model, index, input_ids_d, attention_mask_d, min_length=3, max_length=25, length_penalty=1.0,
+                            num_beams=3, eos_token_id=None, force_decoding_from=None, always_allow_eos=False,
+                            disable_fm_index=False, stop_at_count=0, forced_bos_token_id="config", out=None,
+                            src_tokens=-1, stream=None):
+    """sealdec_generate_dx on DEVICE tensors, asynchronous: input_ids / attention_mask are int64 CUDA tensors
+    [Q, S]; the records land in `out` (a DeviceRecords, created if None) on `stream` (default: the current stream if
+    it is not the legacy default stream, else a per-device side stream that first waits for the current one).
+    `src_tokens`: number of non-zero mask entries if the caller knows it (right-padded masks) — then the call never
+    touches the host; -1 = unknown.  Errors are flags inside the buffer (`out.host()["errors"]`, include/sealdec.h)."""
+    torch = _torch()
+    from .sharding import RecordLayout
+    eng = _engine_for(model)
+    cfg = eng.config
+    if forced_bos_token_id == "config":
+        forced_bos_token_id = getattr(cfg, "forced_bos_token_id", None)
+    if eos_token_id is None:
+        eos_token_id = cfg.eos_token_id
+    if not (input_ids_d.is_cuda and attention_mask_d.is_cuda) or input_ids_d.dtype != torch.int64 or attention_mask_d.dtype != torch.int64:
+        raise TypeError("generate_records_device takes int64 CUDA tensors (use generate_records for host arrays)")
+    ids = input_ids_d.contiguous(); am = attention_mask_d.contiguous()
+    Q, S = ids.shape
+    p = _make_params(cfg, num_beams, min_length, max_length, length_penalty, eos_token_id, force_decoding_from,
+                     always_allow_eos, disable_fm_index, stop_at_count, forced_bos_token_id)
+    H = int(lib.sealdec_hyps_per_query(C.byref(p)))
+    dev = ids.device
+    if out is None:
+        out = DeviceRecords(RecordLayout(Q, H, int(max_length)), dev)
+    lay = out.layout
+    if lay.H != H or lay.T != int(max_length) or lay.Q < Q:
+        raise ValueError("record buffer layout does not fit this call")
+    fm_h = None; occ_ptr = None
+    if not disable_fm_index:
+        if index._device is None:
+            index.to_device(eng.device)
+        fm_h = index._dev()
+        occ = _occurring_mask(index, int(cfg.vocab_size), dev)
+        occ_ptr = occ.data_ptr()
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream()
+        if stream is None:
+            stream = cur if cur.cuda_stream != 0 else _side_stream(dev)
+        if stream.cuda_stream != cur.cuda_stream:
+            stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            out.set_filled(Q)
+            check(lib.sealdec_generate_dx(eng._h, fm_h, occ_ptr, C.byref(p), ids.data_ptr(), am.data_ptr(), Q, S,
+                                          stream.cuda_stream, out.ptr("scores"), out.ptr("lens"), out.ptr("tokens"),
+                                          out.ptr("valid"), out.ptr("lo"), out.ptr("hi"), out.err_ptr, int(src_tokens)))
+        for t in (ids, am, out.buf):
+            t.record_stream(stream)
+        if stream.cuda_stream != cur.cuda_stream:
+            cur.wait_stream(stream)
+    return out
+
+
+def sharded_generate_records(model, index, input_ids, attention_mask, group=None, dst=0, **kw):
+    """N-GPU generate: this rank decodes its contiguous block of the batch (host arrays in, as SEALSearcher holds
+    them), the records stay on the device and ONE NCCL gather brings every rank's buffer to `dst`
+    (SURVEY.md section 8e).  Returns the full-batch record arrays on `dst`, None elsewhere."""
+    torch = _torch()
+    from .sharding import sharded_generate
+    eng = _engine_for(model)
+    dev = torch.device("cuda", eng.device)
+    ids_np = np.ascontiguousarray(np.asarray(input_ids, dtype=np.int64)); am_np = np.ascontiguousarray(np.asarray(attention_mask, dtype=np.int64))
+    cfg = eng.config
+    p = _make_params(cfg, kw.get("num_beams", 3), kw.get("min_length", 3), kw.get("max_length", 25), kw.get("length_penalty", 1.0),
+                     kw.get("eos_token_id") or cfg.eos_token_id, kw.get("force_decoding_from"), False, False, 0, None)
+    H = int(lib.sealdec_hyps_per_query(C.byref(p)))
+
+    def fill(ids_blk, am_blk, layout):
+        rec = DeviceRecords(layout, dev)
+        n = len(ids_blk)
+        if n:
+            right_padded = bool((np.diff(am_blk != 0, axis=1) <= 0).all()) and bool((am_blk[:, 0] != 0).all())
+            generate_records_device(eng, index, torch.from_numpy(ids_blk).to(dev), torch.from_numpy(am_blk).to(dev), out=rec,
+                                    src_tokens=int((am_blk != 0).sum()) if right_padded else -2, **kw)
+        else:
+            rec.set_filled(0)
+        return rec.buf
+
+    return sharded_generate(fill, ids_np, am_np, H, int(kw.get("max_length", 25)), group=group, dst=dst)
+
+
 def records_to_output(rec, length_penalty):
     """beam_search.py:555: [(score * len**lp, tokens) for every recorded hyp with score > -inf].
     The arithmetic is vectorised (float64, like the reference's Python floats; len**lp comes from a table filled

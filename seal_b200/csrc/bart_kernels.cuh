@@ -414,6 +414,38 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
     }
 }
 
+// Decoder self-attention for positions beyond the 32-key register-resident fast path (max_length up to 128,
+// README.md:209-216 decodes with max_length = 100): one warp per (row, head), lane = key inside a 32-key chunk,
+// chunks merged with the online softmax of warp_attend.  Same ancestry indirection, same cache update.
+struct AncestryKV {
+    const float* kc; const float* vc; const int32_t* arow; const float* kcur; const float* vcur;
+    int64_t R; int d; int col; int cur_pos;
+    __device__ __forceinline__ bool valid(int) const { return true; }
+    __device__ __forceinline__ const float* k(int s) const { return s == cur_pos ? kcur : kc + ((int64_t)s * R + arow[s]) * d + col; }
+    __device__ __forceinline__ const float* v(int s) const { return s == cur_pos ? vcur : vc + ((int64_t)s * R + arow[s]) * d + col; }
+};
+
+__global__ void __launch_bounds__(512) dec_self_attn_long_kernel(int64_t R, int d, int heads, int cur_pos, int T,
+                                                                 const float* __restrict__ qkv, float* kc, float* vc,
+                                                                 const int32_t* __restrict__ anc,
+                                                                 float* __restrict__ out, SplitOut so) {
+    __shared__ __align__(16) float q_s[16][kHeadDim];
+    const int64_t r = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* arow = anc + r * T;
+    for (int h = warp; h < heads; h += blockDim.x >> 5) {
+        const int col = h * kHeadDim;
+        const float* qp = qkv + r * 3 * d + col;
+        AncestryKV kv{kc, vc, arow, qp + d, qp + 2 * d, R, d, col, cur_pos};
+        const float2 o = warp_attend(qp, cur_pos + 1, kv, q_s[warp]);
+        store_attn(o, r * d + col + 2 * lane, out, so);
+        const float2 k2 = *reinterpret_cast<const float2*>(qp + d + 2 * lane);
+        const float2 v2 = *reinterpret_cast<const float2*>(qp + 2 * d + 2 * lane);
+        *reinterpret_cast<float2*>(kc + ((int64_t)cur_pos * R + r) * d + col + 2 * lane) = k2;
+        *reinterpret_cast<float2*>(vc + ((int64_t)cur_pos * R + r) * d + col + 2 * lane) = v2;
+    }
+}
+
 // Grouped attention: the `rows` query rows of group g (the beams of one query for cross attention,
 // the tokens of one query for the encoder) all attend to the same n_keys keys, so one CTA per
 // (group, head) stages each 32-key K/V chunk in shared memory ONCE and every warp reuses it

@@ -34,6 +34,10 @@ struct LNp { float* g = nullptr; float* b = nullptr; };
 struct EncLayerW { Lin qkv, o, fc1, fc2; LNp ln_attn, ln_final; };
 struct DecLayerW { Lin qkv, o, cq, ckv, co, fc1, fc2; LNp ln_self, ln_cross, ln_final; };
 
+// Every (re)allocation of a workspace buffer bumps this; a captured CUDA graph bakes buffer addresses in, so
+// graphs captured under an older epoch are discarded.
+uint64_t g_ws_epoch = 0;
+
 struct Buf {
     void* p = nullptr; size_t bytes = 0;
     void ensure(size_t need) {
@@ -41,6 +45,7 @@ struct Buf {
         if (p) { cudaFree(p); p = nullptr; bytes = 0; }
         CUDA_CHECK(cudaMalloc(&p, need));
         bytes = need;
+        ++g_ws_epoch;
     }
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -73,11 +78,24 @@ struct sealbart {
     Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo, splitk;
     std::vector<void*> split_allocs;
     int64_t launches = 0;
+    int* ovf = nullptr;               // where the producers raise "fp16 range exceeded" (set by every entry point)
     double phase_us[5] = {0, 0, 0, 0, 0};
     bool profile_gemm = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
     double gemm_flops = 0;
     std::vector<cudaEvent_t> events;
+    // host-buffer entry point: persistent device staging of the inputs (stable addresses -> CUDA graph reuse)
+    Buf in_ids, in_mask, in_occ;
+    // CUDA graphs of whole generate calls (small batches are launch-latency-bound: ~1 900 kernels per generate)
+    struct GraphEntry { std::vector<uint8_t> key; uint64_t epoch = 0; cudaGraphExec_t exec = nullptr; int64_t launches = 0; uint64_t stamp = 0; };
+    std::vector<GraphEntry> graphs;
+    std::vector<std::vector<uint8_t>> seen_keys;     // shapes run once already (their buffers are sized): capture next time
+    uint64_t graph_stamp = 0;
+    int graph_policy = -1;            // -1 auto (small batches), 0 never, 1 whenever possible
+    int last_used_graph = 0;
+    bool tf32_ready = false;          // 3xTF32 weight splits exist (gemm_mode 2 fallback after an fp16 range overflow)
+    int64_t overflow_fallbacks = 0;
+    cudaStream_t stream = nullptr;    // the host-buffer entry point's own (non-blocking) stream
 };
 
 namespace {
@@ -255,7 +273,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         if (!a1) {
             m->a_hi.ensure((size_t)M * K * 2); m->a_lo.ensure((size_t)M * K * 2);
             const int blocks = (int)std::min<int64_t>(((int64_t)M * K + 255) / 256, (int64_t)sm_count() * 8);
-            split_half_kernel<<<blocks, 256, 0, cx.s>>>((int64_t)M * K, A.x, 1.0f, m->a_hi.as<__half>(), m->a_lo.as<__half>(), m->err.as<int>() + 1);
+            split_half_kernel<<<blocks, 256, 0, cx.s>>>((int64_t)M * K, A.x, 1.0f, m->a_hi.as<__half>(), m->a_lo.as<__half>(), m->ovf);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
             a1 = m->a_hi.as<__half>(); a2 = m->a_lo.as<__half>();
         }
@@ -266,7 +284,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         const int tiles = (int)(((N + kUmmaBN - 1) / kUmmaBN) * ((M + UM - 1) / UM));
         const int ctas = std::min(tiles, sm_count());
         const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;
-        int* ovf = m->err.as<int>() + 1;
+        int* ovf = m->ovf;
         // skinny problems (a few tiles for 148 SMs): split K so that the serial K loop of a tile is spread
         // over up to 8 CTAs, then sum the partial tiles in a fixed order
         const int kblocks = K / (rowb / 2);
@@ -365,7 +383,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
 }
 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
-    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out.x, split_of(out, cx.m->err.as<int>() + 1));
+    add_ln_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, cx.s>>>(rows, d, a, b, ln.g, ln.b, out.x, split_of(out, cx.m->ovf));
     CUDA_CHECK(cudaGetLastError());
     cx.m->launches++;
 }
@@ -382,7 +400,8 @@ __global__ void prep_enc_kernel(int64_t n, int S, const int64_t* __restrict__ id
 // Source lengths, their exclusive prefix sum (src_off[Q+1]) and whether every mask row is "ones then zeros"
 // (right padding) -- the precondition for running the encoder on the real tokens only.  One block.
 __global__ void __launch_bounds__(1024) pack_lengths_kernel(int64_t Q, int S, const int64_t* __restrict__ mask,
-                                                            int32_t* __restrict__ src_off, int64_t* __restrict__ info) {
+                                                            int32_t* __restrict__ src_off, int64_t* __restrict__ info,
+                                                            int64_t hint, int32_t* __restrict__ hint_err) {
     __shared__ int64_t part[1024];
     __shared__ int bad;
     const int t = threadIdx.x;
@@ -398,7 +417,12 @@ __global__ void __launch_bounds__(1024) pack_lengths_kernel(int64_t Q, int S, co
     part[t] = sum;
     if (notprefix) atomicExch(&bad, 1);
     __syncthreads();
-    if (t == 0) { int64_t run = 0; for (int i = 0; i < 1024; ++i) { const int64_t v = part[i]; part[i] = run; run += v; } info[0] = run; info[1] = bad; }
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; ++i) { const int64_t v = part[i]; part[i] = run; run += v; }
+        info[0] = run; info[1] = bad;
+        if (hint >= 0 && hint_err && (run != hint || bad)) *hint_err = 1;      // the caller's token count was wrong
+    }
     __syncthreads();
     int64_t run = part[t];
     for (int64_t q = q0; q < q1; ++q) {
@@ -462,10 +486,14 @@ void ensure_workspace(sealbart* m, const Dims& D) {
         m->dattn_hi.ensure(D.R * D.d * 4); m->dattn_lo.ensure(D.R * D.d * 4);
         m->dffn_hi.ensure(D.R * D.f * 4); m->dffn_lo.ensure(D.R * D.f * 4);
     }
-    m->err.ensure(8);
+    m->err.ensure(16);
 }
 
-void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t* mask_d) {
+// src_tokens_hint: >= 0 the caller's count of real source tokens (right-padded masks): no host synchronisation, the
+// kernel that derives the offsets checks it and raises err_d[2] on a mismatch; -1 unknown: one 16-byte read-back;
+// -2 do not pack (padded rows are computed; also no synchronisation).
+void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t* mask_d, int64_t src_tokens_hint = -1,
+                     int32_t* hint_err = nullptr) {
     sealbart* m = cx.m;
     const int64_t Tk = D.Q * D.S;
     const int d = D.d;
@@ -478,13 +506,16 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     int64_t* info_d = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(m->src_off.p) + ((D.Q + 1) * 4 + 15) / 16 * 16);
     int64_t rows_enc = Tk;
     m->enc_packed = false;
-    if (pack_enabled) {
-        pack_lengths_kernel<<<1, 1024, 0, cx.s>>>(D.Q, (int)D.S, mask_d, src_off, info_d);
+    if (pack_enabled && src_tokens_hint != -2) {
+        pack_lengths_kernel<<<1, 1024, 0, cx.s>>>(D.Q, (int)D.S, mask_d, src_off, info_d, src_tokens_hint, hint_err);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
-        int64_t info[2] = {0, 1};
-        CUDA_CHECK(cudaMemcpyAsync(info, info_d, 16, cudaMemcpyDeviceToHost, cx.s));
-        CUDA_CHECK(cudaStreamSynchronize(cx.s));
-        if (info[1] == 0 && info[0] > 0) { m->enc_packed = true; rows_enc = info[0]; }
+        if (src_tokens_hint > 0) { m->enc_packed = true; rows_enc = src_tokens_hint; }
+        else {
+            int64_t info[2] = {0, 1};
+            CUDA_CHECK(cudaMemcpyAsync(info, info_d, 16, cudaMemcpyDeviceToHost, cx.s));
+            CUDA_CHECK(cudaStreamSynchronize(cx.s));
+            if (info[1] == 0 && info[0] > 0) { m->enc_packed = true; rows_enc = info[0]; }
+        }
     }
     const int32_t* soff = m->enc_packed ? src_off : nullptr;
     if (m->enc_packed) prep_enc_packed_kernel<<<(unsigned)((Tk + 255) / 256), 256, 0, cx.s>>>(Tk, (int)D.S, ids_d, src_off, tok, pos);
@@ -499,7 +530,7 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
         if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
-    int* ovf = m->err.as<int>() + 1;
+    int* ovf = m->ovf;
     const Act x = mk(m->ex.as<float>(), m->ex_hi, m->ex_lo, true);
     const Act qkv{m->eqkv.as<float>()};
     const Act attn = mk(m->eattn.as<float>(), m->eattn_hi, m->eattn_lo, false);
@@ -547,7 +578,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
-    int* ovf = m->err.as<int>() + 1;
+    int* ovf = m->ovf;
     const Act x = mk(m->dx.as<float>(), m->dx_hi, m->dx_lo, true);
     const Act qkv{m->dqkv.as<float>()};
     const Act attn = mk(m->dattn.as<float>(), m->dattn_hi, m->dattn_lo, false);
@@ -568,9 +599,12 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         if (pos + 1 <= 12)
             dec_self_attn_kernel<3><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(Rc, d, heads, pos, D.T, qkv.x, kc, vc, anc,
                                                                                       attn.x, split_of(attn, ovf), row_mul, row_mul);
-        else
+        else if (pos + 1 <= 32)
             dec_self_attn_kernel<8><<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(Rc, d, heads, pos, D.T, qkv.x, kc, vc, anc,
                                                                                       attn.x, split_of(attn, ovf), row_mul, row_mul);
+        else
+            dec_self_attn_long_kernel<<<(unsigned)R, 32 * std::min(heads, 16), 0, cx.s>>>(Rc, d, heads, pos, D.T, qkv.x, kc, vc, anc,
+                                                                                         attn.x, split_of(attn, ovf));
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
@@ -615,6 +649,28 @@ cudaEvent_t new_event(sealbart* m) {
     cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); m->events.push_back(e); return e;
 }
 
+
+template <typename Fn> void for_each_lin(sealbart* m, Fn&& fn) {
+    for (auto& L : m->enc) { fn(L.qkv); fn(L.o); fn(L.fc1); fn(L.fc2); }
+    for (auto& L : m->dec) { fn(L.qkv); fn(L.o); fn(L.cq); fn(L.ckv); fn(L.co); fn(L.fc1); fn(L.fc2); }
+    fn(m->head);
+}
+
+// 3xTF32 operand copies of every weight matrix (gemm_mode 1 / 2; also the range-safe fallback of the 3xFP16 modes)
+void ensure_tf32_splits(sealbart* m) {
+    if (m->tf32_ready) return;
+    CUDA_CHECK(cudaSetDevice(m->device));
+    for_each_lin(m, [&](Lin& l) {
+        const uint64_t n = (uint64_t)l.out * l.in;
+        CUDA_CHECK(cudaMalloc(&l.w_hi, n * 4)); m->split_allocs.push_back(l.w_hi);
+        CUDA_CHECK(cudaMalloc(&l.w_lo, n * 4)); m->split_allocs.push_back(l.w_lo);
+        split_into(nullptr, l.w, l.w_hi, l.w_lo, n);
+        m->weight_bytes += 2 * n * 4;
+    });
+    CUDA_CHECK(cudaDeviceSynchronize());
+    m->tf32_ready = true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -651,6 +707,9 @@ void sealbart_free(sealbart_t* m) {
                    &m->dffn_hi, &m->dffn_lo, &m->splitk})
         b->release();
     for (auto e : m->events) cudaEventDestroy(e);
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (Buf* b : {&m->in_ids, &m->in_mask, &m->in_occ}) b->release();
+    if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
 
@@ -687,16 +746,10 @@ int sealbart_finalize(sealbart_t* m) {
             CUDA_CHECK(cudaSetDevice(m->device));
             for (void* p : m->split_allocs) cudaFree(p);
             m->split_allocs.clear();
-            auto split_lin = [&](Lin& l) {
-                const uint64_t n = (uint64_t)l.out * l.in;
-                CUDA_CHECK(cudaMalloc(&l.w_hi, n * 4)); m->split_allocs.push_back(l.w_hi);
-                CUDA_CHECK(cudaMalloc(&l.w_lo, n * 4)); m->split_allocs.push_back(l.w_lo);
-                split_into(nullptr, l.w, l.w_hi, l.w_lo, n);
-                l.maps_ready = false;
-                m->weight_bytes += 2 * n * 4;
-            };
+            m->tf32_ready = false;
+            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; });
             unsigned int* d_max = nullptr;
-            if (m->cfg.gemm_mode >= 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(8); CUDA_CHECK(cudaMemset(m->err.p, 0, 8)); }
+            if (m->cfg.gemm_mode >= 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(16); CUDA_CHECK(cudaMemset(m->err.p, 0, 16)); }
             auto split_lin_half = [&](Lin& l) {
                 const uint64_t n = (uint64_t)l.out * l.in;
                 CUDA_CHECK(cudaMemset(d_max, 0, 4));
@@ -722,10 +775,7 @@ int sealbart_finalize(sealbart_t* m) {
                 m->finalized = true;
                 return;
             }
-            for (auto& L : m->enc) { split_lin(L.qkv); split_lin(L.o); split_lin(L.fc1); split_lin(L.fc2); }
-            for (auto& L : m->dec) { split_lin(L.qkv); split_lin(L.o); split_lin(L.cq); split_lin(L.ckv); split_lin(L.co); split_lin(L.fc1); split_lin(L.fc2); }
-            split_lin(m->head);
-            CUDA_CHECK(cudaDeviceSynchronize());
+            ensure_tf32_splits(m);
         }
         m->finalized = true;
     });
@@ -738,18 +788,135 @@ int64_t sealdec_hyps_per_query(const sealdec_params_t* p) {
     return (int64_t)(p->max_length - 1) * 2 * p->num_beams + p->num_beams;
 }
 
-int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d, const sealdec_params_t* p,
-                       const int64_t* ids_d, const int64_t* mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
-                       float* o_score, int32_t* o_len, int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo,
-                       uint64_t* o_hi, int32_t* err_d) {
+
+}  // extern "C"
+
+namespace {
+
+struct GenArgs {
+    const sealfm_t* fm; const uint32_t* occ_d; const sealdec_params_t* p;
+    const int64_t* ids_d; const int64_t* mask_d; int64_t Q, S;
+    float* o_score; int32_t* o_len; int32_t* o_tok; uint8_t* o_valid; uint64_t* o_lo; uint64_t* o_hi; int32_t* err_d;
+};
+
+// Enqueues one whole generate (encoder, every decode step, records) on cx.s.  No host synchronisation unless
+// src_hint == -1.  `timing` = bracket the phases with CUDA events (not possible while the stream is being captured).
+void generate_enqueue(Ctx& cx, const Dims& D, const GenArgs& a, const FmView& view, uint64_t lo0, uint64_t hi0,
+                      int64_t src_hint, bool timing) {
+    sealbart* m = cx.m;
+    const sealdec_params_t* p = a.p;
+    const int B = D.B, K = 2 * B, T = D.T;
+    const int64_t Q = D.Q, R = D.R;
+    for (auto e : m->events) cudaEventDestroy(e);
+    m->events.clear();
+    auto mark = [&]() -> cudaEvent_t {
+        if (!timing) return nullptr;
+        cudaEvent_t e = new_event(m);
+        CUDA_CHECK(cudaEventRecord(e, cx.s));
+        return e;
+    };
+    CUDA_CHECK(cudaMemsetAsync(a.err_d, 0, 16, cx.s));
+    mark();
+    encoder_forward(cx, D, a.ids_d, a.mask_d, src_hint, a.err_d + 2);
+    mark();
+
+    float* sc[2] = {m->st_scores.as<float>(), m->st_scores.as<float>() + R};
+    int32_t* tk[2] = {m->st_tokens.as<int32_t>(), m->st_tokens.as<int32_t>() + R * T};
+    uint64_t* lo[2] = {m->st_lo.as<uint64_t>(), m->st_lo.as<uint64_t>() + R};
+    uint64_t* hi[2] = {m->st_hi.as<uint64_t>(), m->st_hi.as<uint64_t>() + R};
+    uint64_t* pw[2] = {m->st_pw.as<uint64_t>(), m->st_pw.as<uint64_t>() + R};
+    int32_t* an[2] = {m->st_anc.as<int32_t>(), m->st_anc.as<int32_t>() + R * T};
+    uint32_t* mk[2] = {m->st_mask.as<uint32_t>(), m->st_mask.as<uint32_t>() + (size_t)R * D.W};
+    init_state_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(R, B, T, p->decoder_start_token_id, p->pad_token_id,
+                                                                    lo0, hi0, sc[0], tk[0], lo[0], hi[0], pw[0], an[0]);
+    CUDA_CHECK(cudaGetLastError()); m->launches++;
+
+    StepCfg c{};
+    c.num_beams = B; c.K = K; c.V = D.V; c.ld = D.ld;
+    c.min_length = p->min_length; c.max_length = p->max_length;
+    c.eos_token_id = p->eos_token_id; c.pad_token_id = p->pad_token_id; c.model_eos_token_id = p->model_eos_token_id;
+    c.forced_eos_token_id = p->forced_eos_token_id; c.forced_bos_token_id = p->forced_bos_token_id;
+    c.stop_at_count = p->stop_at_count; c.always_allow_eos = p->always_allow_eos; c.disable_fm_index = p->disable_fm_index;
+    c.remove_invalid_values = p->remove_invalid_values; c.shift = p->shift; c.T = T; c.mask_words = D.W;
+    c.hyps_per_query = sealdec_hyps_per_query(p);
+    CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+    int cur = 0;
+    for (int step = 0; step + 1 < T; ++step) {
+        const int cur_len = step + 1;
+        mark();
+        static const bool compact_first = [] { const char* e = std::getenv("SEALB200_COMPACT_FIRST"); return !e || std::atoi(e) != 0; }();
+        const bool compact = compact_first && cur_len == 1;
+        // Dead step: when ForcedEOSTokenLogitsProcessor fires (cur_len == max_length - 1, HF semantics restated
+        // in apply_processors) it overwrites EVERY processed score with a constant, so neither the recorded
+        // hypotheses nor the (already final) beams depend on the model output of this step -- the reference
+        // computes it and discards it.  Nothing later reads this position's k / v either.
+        static const bool skip_dead = [] { const char* e = std::getenv("SEALB200_SKIP_DEAD_STEP"); return !e || std::atoi(e) != 0; }();
+        const bool forced_all = p->forced_eos_token_id >= 0 && cur_len == p->max_length - 1 && cur_len + 1 == T &&
+                                !(p->forced_bos_token_id >= 0 && cur_len == 1);
+        const bool dead = skip_dead && forced_all;
+        cudaEvent_t b = timing ? new_event(m) : nullptr;
+        if (!dead) decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b, compact);
+        else if (b) CUDA_CHECK(cudaEventRecord(b, cx.s));
+        mark();
+        c.cur_len = cur_len;
+        c.logits_shared = (compact && !dead) ? 1 : 0;
+        c.logits_ignored = dead ? 1 : 0;
+        const int eff_len = cur_len - (p->forced_bos_token_id >= 0 ? 1 : 0);
+        c.first_step_shared_mask = (!p->disable_fm_index && eff_len == 1) ? 1 : 0;
+        c.expand_next = (cur_len + 1 < T) ? 1 : 0;
+        c.hyp_base = step * K;
+        StepState st{};
+        st.beam_scores_in = sc[cur]; st.beam_scores_out = sc[cur ^ 1];
+        st.tokens_in = tk[cur]; st.tokens_out = tk[cur ^ 1];
+        st.lo_in = lo[cur]; st.lo_out = lo[cur ^ 1]; st.hi_in = hi[cur]; st.hi_out = hi[cur ^ 1];
+        st.pw_in = pw[cur]; st.pw_out = pw[cur ^ 1];
+        st.anc_in = an[cur]; st.anc_out = an[cur ^ 1];
+        st.mask_in = mk[cur]; st.mask_out = mk[cur ^ 1];
+        st.occurring_mask = a.occ_d; st.logits = m->logits.as<float>();
+        st.hyp_score = a.o_score; st.hyp_len = a.o_len; st.hyp_tokens = a.o_tok; st.hyp_valid = a.o_valid;
+        st.hyp_lo = a.o_lo; st.hyp_hi = a.o_hi; st.error_flag = a.err_d;
+        select_step_kernel<0><<<(unsigned)Q, kSelThreads, sizeof(SelShared), cx.s>>>(view, c, st);
+        CUDA_CHECK(cudaGetLastError()); m->launches++;
+        mark();
+        cur ^= 1;
+    }
+    c.cur_len = T; c.hyp_base = (T - 1) * K;
+    StepState st{};
+    st.hyp_score = a.o_score; st.hyp_len = a.o_len; st.hyp_tokens = a.o_tok; st.hyp_valid = a.o_valid; st.hyp_lo = a.o_lo; st.hyp_hi = a.o_hi;
+    finalize_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(Q, c, sc[cur], tk[cur], lo[cur], hi[cur], st);
+    CUDA_CHECK(cudaGetLastError()); m->launches++;
+    mark();
+    // events in creation order: ev0, ev_enc, then per step a, b, c, d, then end (sealdec_last_phase_us)
+}
+
+template <typename T> void key_put(std::vector<uint8_t>& k, const T& v) {
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(&v);
+    k.insert(k.end(), b, b + sizeof(T));
+}
+
+void drop_graphs(sealbart* m) {
+    for (auto& g : m->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    m->graphs.clear();
+    m->seen_keys.clear();
+}
+
+}  // namespace
+
+extern "C" {
+
+int sealdec_generate_dx(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d, const sealdec_params_t* p,
+                        const int64_t* ids_d, const int64_t* mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
+                        float* o_score, int32_t* o_len, int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo,
+                        uint64_t* o_hi, int32_t* err_d, int64_t src_tokens_hint) {
     return guarded([&] {
         check_model(m);
-        if (!p || !ids_d || !mask_d || !o_score || !o_len || !o_tok || !o_valid) throw ApiError(SEALFM_EINVAL, "null argument");
+        if (!p || !ids_d || !mask_d || !o_score || !o_len || !o_tok || !o_valid || !err_d) throw ApiError(SEALFM_EINVAL, "null argument");
         const int B = p->num_beams, K = 2 * B, T = p->max_length;
         if (B < 1 || B > kSelMaxBeams || K > kSelMaxK) throw ApiError(SEALFM_EINVAL, "num_beams must be in [1,32]");
-        if (T < 2 || T > kMaxLen) throw ApiError(SEALFM_EINVAL, "max_length must be in [2,32]");
+        if (T < 2 || T > kMaxLen) throw ApiError(SEALFM_EINVAL, "max_length must be in [2,128]");
         if (Q <= 0 || S <= 0) throw ApiError(SEALFM_EINVAL, "empty batch");
         if (S > m->cfg.max_positions) throw ApiError(SEALFM_EINVAL, "source longer than max_positions");
+        if (src_tokens_hint < -2 || src_tokens_hint > Q * S) throw ApiError(SEALFM_EINVAL, "bad source-token hint");
         FmView view{};
         uint64_t lo0 = 0, hi0 = 0;
         if (!p->disable_fm_index) {
@@ -766,92 +933,115 @@ int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d,
         }
         Ctx cx{m, (cudaStream_t)stream};
         m->launches = 0;
+        m->ovf = err_d + 1;
+        m->last_used_graph = 0;
         const Dims D = make_dims(m, Q, S, B, T);
         ensure_workspace(m, D);
-        for (auto e : m->events) cudaEventDestroy(e);
-        m->events.clear();
-        cudaEvent_t ev0 = new_event(m), ev_enc = new_event(m);
-        CUDA_CHECK(cudaEventRecord(ev0, cx.s));
-        encoder_forward(cx, D, ids_d, mask_d);
-        CUDA_CHECK(cudaEventRecord(ev_enc, cx.s));
+        const GenArgs a{fm, occ_d, p, ids_d, mask_d, Q, S, o_score, o_len, o_tok, o_valid, o_lo, o_hi, err_d};
 
-        const int64_t R = D.R;
-        float* sc[2] = {m->st_scores.as<float>(), m->st_scores.as<float>() + R};
-        int32_t* tk[2] = {m->st_tokens.as<int32_t>(), m->st_tokens.as<int32_t>() + R * T};
-        uint64_t* lo[2] = {m->st_lo.as<uint64_t>(), m->st_lo.as<uint64_t>() + R};
-        uint64_t* hi[2] = {m->st_hi.as<uint64_t>(), m->st_hi.as<uint64_t>() + R};
-        uint64_t* pw[2] = {m->st_pw.as<uint64_t>(), m->st_pw.as<uint64_t>() + R};
-        int32_t* an[2] = {m->st_anc.as<int32_t>(), m->st_anc.as<int32_t>() + R * T};
-        uint32_t* mk[2] = {m->st_mask.as<uint32_t>(), m->st_mask.as<uint32_t>() + (size_t)R * D.W};
-        init_state_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(R, B, T, p->decoder_start_token_id, p->pad_token_id,
-                                                                        lo0, hi0, sc[0], tk[0], lo[0], hi[0], pw[0], an[0]);
-        CUDA_CHECK(cudaGetLastError()); m->launches++;
-        CUDA_CHECK(cudaMemsetAsync(err_d, 0, 4, cx.s));
-        CUDA_CHECK(cudaMemsetAsync(m->err.as<int>() + 1, 0, 4, cx.s));
+        // ---- CUDA graph of the whole call: a batch-20 generate is ~1 900 short kernels, i.e. launch-latency-bound.
+        // Shapes, parameters and buffer addresses are the key; the first call of a key runs eagerly (it sizes every
+        // lazily grown buffer), the second is captured, later ones are one cudaGraphLaunch.
+        static const int env_graph = [] { const char* e = std::getenv("SEALB200_GRAPH"); return e ? std::atoi(e) : -1; }();
+        const int policy = m->graph_policy >= 0 ? m->graph_policy : env_graph;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cx.s) CUDA_CHECK(cudaStreamIsCapturing(cx.s, &cap));
+        const bool small = D.R <= 4096;
+        bool want_graph = cx.s != nullptr && cap == cudaStreamCaptureStatusNone && !m->profile_gemm &&
+                          (policy == 1 || (policy < 0 && small));
+        // inside a graph the encoder never needs the host: small batches compute the padded rows (the key then does
+        // not depend on the batch's contents), larger ones use the caller's token count
+        int64_t eff_hint = src_tokens_hint;
+        if (want_graph) { if (small) eff_hint = -2; else if (src_tokens_hint == -1) want_graph = false; }
+        if (!want_graph) { generate_enqueue(cx, D, a, view, lo0, hi0, eff_hint, cap == cudaStreamCaptureStatusNone); m->phase_us[0] = -1; return; }
 
-        StepCfg c{};
-        c.num_beams = B; c.K = K; c.V = D.V; c.ld = D.ld;
-        c.min_length = p->min_length; c.max_length = p->max_length;
-        c.eos_token_id = p->eos_token_id; c.pad_token_id = p->pad_token_id; c.model_eos_token_id = p->model_eos_token_id;
-        c.forced_eos_token_id = p->forced_eos_token_id; c.forced_bos_token_id = p->forced_bos_token_id;
-        c.stop_at_count = p->stop_at_count; c.always_allow_eos = p->always_allow_eos; c.disable_fm_index = p->disable_fm_index;
-        c.remove_invalid_values = p->remove_invalid_values; c.shift = p->shift; c.T = T; c.mask_words = D.W;
-        c.hyps_per_query = sealdec_hyps_per_query(p);
-        CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
-        std::vector<cudaEvent_t> ev_a, ev_b, ev_c, ev_d;
-        int cur = 0;
-        for (int step = 0; step + 1 < T; ++step) {
-            const int cur_len = step + 1;
-            cudaEvent_t a = new_event(m), b = new_event(m), cc = new_event(m), dd = new_event(m);
-            CUDA_CHECK(cudaEventRecord(a, cx.s));
-            static const bool compact_first = [] { const char* e = std::getenv("SEALB200_COMPACT_FIRST"); return !e || std::atoi(e) != 0; }();
-            const bool compact = compact_first && cur_len == 1;
-            // Dead step: when ForcedEOSTokenLogitsProcessor fires (cur_len == max_length - 1, HF semantics restated
-            // in apply_processors) it overwrites EVERY processed score with a constant, so neither the recorded
-            // hypotheses nor the (already final) beams depend on the model output of this step -- the reference
-            // computes it and discards it.  Nothing later reads this position's k / v either.
-            static const bool skip_dead = [] { const char* e = std::getenv("SEALB200_SKIP_DEAD_STEP"); return !e || std::atoi(e) != 0; }();
-            const bool forced_all = p->forced_eos_token_id >= 0 && cur_len == p->max_length - 1 && cur_len + 1 == T &&
-                                    !(p->forced_bos_token_id >= 0 && cur_len == 1);
-            const bool dead = skip_dead && forced_all;
-            if (!dead) decoder_step(cx, D, tk[cur], cur_len, an[cur], true, b, compact);
-            else CUDA_CHECK(cudaEventRecord(b, cx.s));
-            CUDA_CHECK(cudaEventRecord(cc, cx.s));
-            c.cur_len = cur_len;
-            c.logits_shared = (compact && !dead) ? 1 : 0;
-            c.logits_ignored = dead ? 1 : 0;
-            const int eff_len = cur_len - (p->forced_bos_token_id >= 0 ? 1 : 0);
-            c.first_step_shared_mask = (!p->disable_fm_index && eff_len == 1) ? 1 : 0;
-            c.expand_next = (cur_len + 1 < T) ? 1 : 0;
-            c.hyp_base = step * K;
-            StepState st{};
-            st.beam_scores_in = sc[cur]; st.beam_scores_out = sc[cur ^ 1];
-            st.tokens_in = tk[cur]; st.tokens_out = tk[cur ^ 1];
-            st.lo_in = lo[cur]; st.lo_out = lo[cur ^ 1]; st.hi_in = hi[cur]; st.hi_out = hi[cur ^ 1];
-            st.pw_in = pw[cur]; st.pw_out = pw[cur ^ 1];
-            st.anc_in = an[cur]; st.anc_out = an[cur ^ 1];
-            st.mask_in = mk[cur]; st.mask_out = mk[cur ^ 1];
-            st.occurring_mask = occ_d; st.logits = m->logits.as<float>();
-            st.hyp_score = o_score; st.hyp_len = o_len; st.hyp_tokens = o_tok; st.hyp_valid = o_valid;
-            st.hyp_lo = o_lo; st.hyp_hi = o_hi; st.error_flag = err_d;
-            select_step_kernel<0><<<(unsigned)Q, kSelThreads, sizeof(SelShared), cx.s>>>(view, c, st);
-            CUDA_CHECK(cudaGetLastError()); m->launches++;
-            CUDA_CHECK(cudaEventRecord(dd, cx.s));
-            ev_a.push_back(a); ev_b.push_back(b); ev_c.push_back(cc); ev_d.push_back(dd);
-            cur ^= 1;
+        std::vector<uint8_t> key;
+        key_put(key, Q); key_put(key, S); key_put(key, eff_hint); key_put(key, lo0); key_put(key, hi0);
+        key_put(key, m->cfg.gemm_mode); key_put(key, cx.s);
+        sealdec_params_t pc = *p; pc.force_decoding_from = nullptr; key_put(key, pc);
+        for (int i = 0; i < p->n_force_decoding_from; ++i) key_put(key, p->force_decoding_from[i]);
+        key_put(key, view.blocks); key_put(key, view.csym); key_put(key, view.node_tab); key_put(key, view.m);
+        key_put(key, occ_d); key_put(key, ids_d); key_put(key, mask_d); key_put(key, o_score); key_put(key, o_len);
+        key_put(key, o_tok); key_put(key, o_valid); key_put(key, o_lo); key_put(key, o_hi); key_put(key, err_d);
+        if (!m->graphs.empty() && m->graphs.front().epoch != g_ws_epoch) drop_graphs(m);
+        for (auto& g : m->graphs)
+            if (g.key == key) {
+                CUDA_CHECK(cudaGraphLaunch(g.exec, cx.s));
+                g.stamp = ++m->graph_stamp; m->launches = g.launches; m->last_used_graph = 1;
+                return;
+            }
+        bool seen = false;
+        for (auto& k2 : m->seen_keys) if (k2 == key) { seen = true; break; }
+        if (!seen) {                                           // first time: eager (sizes split-K / staging buffers)
+            if (m->seen_keys.size() >= 16) m->seen_keys.erase(m->seen_keys.begin());
+            m->seen_keys.push_back(key);
+            generate_enqueue(cx, D, a, view, lo0, hi0, eff_hint, true);
+            m->phase_us[0] = -1;
+            return;
         }
-        c.cur_len = T; c.hyp_base = (T - 1) * K;
-        StepState st{};
-        st.hyp_score = o_score; st.hyp_len = o_len; st.hyp_tokens = o_tok; st.hyp_valid = o_valid; st.hyp_lo = o_lo; st.hyp_hi = o_hi;
-        finalize_kernel<<<(unsigned)((R + 255) / 256), 256, 0, cx.s>>>(Q, c, sc[cur], tk[cur], lo[cur], hi[cur], st);
-        CUDA_CHECK(cudaGetLastError()); m->launches++;
-        cudaEvent_t ev_end = new_event(m);
-        CUDA_CHECK(cudaEventRecord(ev_end, cx.s));
-        // phase accounting is resolved lazily in sealdec_last_phase_us (needs the stream to drain)
-        m->phase_us[0] = -1;
-        // stash event handles in order: ev0, ev_enc, then per step a,b,c,d, then end
-        // (m->events already holds them in creation order)
+        const uint64_t epoch0 = g_ws_epoch;
+        cudaGraph_t graph = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(cx.s, cudaStreamCaptureModeRelaxed));
+        try { generate_enqueue(cx, D, a, view, lo0, hi0, eff_hint, false); }
+        catch (...) { cudaStreamEndCapture(cx.s, &graph); if (graph) cudaGraphDestroy(graph); throw; }
+        CUDA_CHECK(cudaStreamEndCapture(cx.s, &graph));
+        if (g_ws_epoch != epoch0) {                            // a buffer moved while capturing: the graph is stale
+            cudaGraphDestroy(graph);
+            m->launches = 0;
+            generate_enqueue(cx, D, a, view, lo0, hi0, eff_hint, true);
+            m->phase_us[0] = -1;
+            return;
+        }
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { cudaGetLastError(); throw ApiError(SEALFM_ECUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
+        if (m->graphs.size() >= 8) {                           // evict the least recently used
+            size_t victim = 0;
+            for (size_t i = 1; i < m->graphs.size(); ++i) if (m->graphs[i].stamp < m->graphs[victim].stamp) victim = i;
+            cudaGraphExecDestroy(m->graphs[victim].exec);
+            m->graphs.erase(m->graphs.begin() + victim);
+        }
+        sealbart::GraphEntry ge; ge.key = std::move(key); ge.epoch = g_ws_epoch; ge.exec = exec; ge.launches = m->launches; ge.stamp = ++m->graph_stamp;
+        m->graphs.push_back(std::move(ge));
+        CUDA_CHECK(cudaGraphLaunch(exec, cx.s));
+        m->last_used_graph = 1;
     });
+}
+
+int sealdec_generate_d(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d, const sealdec_params_t* p,
+                       const int64_t* ids_d, const int64_t* mask_d, int64_t Q, int64_t S, sealfm_stream_t stream,
+                       float* o_score, int32_t* o_len, int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo,
+                       uint64_t* o_hi, int32_t* err_d) {
+    return sealdec_generate_dx(m, fm, occ_d, p, ids_d, mask_d, Q, S, stream, o_score, o_len, o_tok, o_valid, o_lo, o_hi, err_d, -1);
+}
+
+int sealbart_set_option(sealbart_t* m, const char* name, int64_t value) {
+    return guarded([&] {
+        if (!m || !name) throw ApiError(SEALFM_EINVAL, "null argument");
+        const std::string n(name);
+        if (n == "cuda_graph") { if (value < -1 || value > 1) throw ApiError(SEALFM_EINVAL, "cuda_graph: -1 auto, 0 off, 1 on"); m->graph_policy = (int)value; }
+        else if (n == "gemm_mode") {
+            check_model(m);
+            if (value == m->cfg.gemm_mode) return;
+            if (value == 2 && m->cfg.gemm_mode >= 3) { ensure_tf32_splits(m); m->cfg.gemm_mode = 2; }
+            else if (value >= 3 && value <= 5 && m->head.w_h1) m->cfg.gemm_mode = (int)value;
+            else throw ApiError(SEALFM_EINVAL, "gemm_mode can only switch between the 3xFP16 modes (3, 4, 5) and 2 (3xTF32)");
+            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; });
+            drop_graphs(m);
+        }
+        else throw ApiError(SEALFM_EINVAL, "unknown option: " + n);
+    });
+}
+
+int64_t sealbart_get_stat(const sealbart_t* m, const char* name) {
+    if (!m || !name) return -1;
+    const std::string n(name);
+    if (n == "last_used_graph") return m->last_used_graph;
+    if (n == "overflow_fallbacks") return m->overflow_fallbacks;
+    if (n == "gemm_mode") return m->cfg.gemm_mode;
+    if (n == "cached_graphs") return (int64_t)m->graphs.size();
+    return -1;
 }
 
 int sealdec_last_phase_us(const sealbart_t* mc, double out5[5]) {
@@ -905,35 +1095,61 @@ int sealdec_generate(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_host
                      int32_t* o_tok, uint8_t* o_valid, uint64_t* o_lo, uint64_t* o_hi) {
     return guarded([&] {
         check_model(m);
-        if (!p || !ids || !mask) throw ApiError(SEALFM_EINVAL, "null argument");
+        if (!p || !ids || !mask || Q <= 0 || S <= 0) throw ApiError(SEALFM_EINVAL, "null argument / empty batch");
         const int64_t H = sealdec_hyps_per_query(p), T = p->max_length;
         const int W = (m->cfg.vocab_size + 31) / 32;
-        Buf d_ids, d_mask, d_occ;
-        d_ids.ensure(Q * S * 8); d_mask.ensure(Q * S * 8); d_occ.ensure((size_t)W * 4);
-        struct Rel { Buf *a, *b, *c; ~Rel() { a->release(); b->release(); c->release(); } } rel{&d_ids, &d_mask, &d_occ};
-        cudaStream_t s = nullptr;
-        CUDA_CHECK(cudaMemcpyAsync(d_ids.p, ids, Q * S * 8, cudaMemcpyHostToDevice, s));
-        CUDA_CHECK(cudaMemcpyAsync(d_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
-        if (occ_host) CUDA_CHECK(cudaMemcpyAsync(d_occ.p, occ_host, (size_t)W * 4, cudaMemcpyHostToDevice, s));
+        // the caller's buffers are host memory: the real-token count costs nothing to know here, so the encoder
+        // never has to ask the device for it (right-padded masks only; anything else takes the padded path)
+        int64_t hint = 0;
+        for (int64_t q = 0; q < Q && hint >= 0; ++q) {
+            int64_t len = 0;
+            for (int64_t s2 = 0; s2 < S; ++s2) { const bool on = mask[q * S + s2] != 0; if (on && s2 != len) { hint = -2; break; } len += on; }
+            if (hint >= 0) hint += len;
+        }
+        if (hint == 0) hint = -2;
+        if (!m->stream) CUDA_CHECK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        cudaStream_t s = m->stream;
+        m->in_ids.ensure(Q * S * 8); m->in_mask.ensure(Q * S * 8); m->in_occ.ensure((size_t)W * 4);
         m->hy_score.ensure(Q * H * 4); m->hy_len.ensure(Q * H * 4); m->hy_tok.ensure(Q * H * T * 4);
-        m->hy_valid.ensure(Q * H); m->hy_lo.ensure(Q * H * 8); m->hy_hi.ensure(Q * H * 8); m->err.ensure(8);
-        int rc = sealdec_generate_d(m, fm, occ_host ? d_occ.as<uint32_t>() : nullptr, p, d_ids.as<int64_t>(), d_mask.as<int64_t>(),
-                                    Q, S, s, m->hy_score.as<float>(), m->hy_len.as<int32_t>(), m->hy_tok.as<int32_t>(),
-                                    m->hy_valid.as<uint8_t>(), o_lo ? m->hy_lo.as<uint64_t>() : nullptr,
-                                    o_hi ? m->hy_hi.as<uint64_t>() : nullptr, m->err.as<int32_t>());
-        if (rc) throw ApiError(rc, last_error());
+        m->hy_valid.ensure(Q * H); m->hy_lo.ensure(Q * H * 8); m->hy_hi.ensure(Q * H * 8); m->err.ensure(16);
+        CUDA_CHECK(cudaMemcpyAsync(m->in_ids.p, ids, Q * S * 8, cudaMemcpyHostToDevice, s));
+        CUDA_CHECK(cudaMemcpyAsync(m->in_mask.p, mask, Q * S * 8, cudaMemcpyHostToDevice, s));
+        if (occ_host) CUDA_CHECK(cudaMemcpyAsync(m->in_occ.p, occ_host, (size_t)W * 4, cudaMemcpyHostToDevice, s));
+        int32_t errs[4] = {0, 0, 0, 0};
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            int rc = sealdec_generate_dx(m, fm, occ_host ? m->in_occ.as<uint32_t>() : nullptr, p, m->in_ids.as<int64_t>(),
+                                         m->in_mask.as<int64_t>(), Q, S, s, m->hy_score.as<float>(), m->hy_len.as<int32_t>(),
+                                         m->hy_tok.as<int32_t>(), m->hy_valid.as<uint8_t>(), o_lo ? m->hy_lo.as<uint64_t>() : nullptr,
+                                         o_hi ? m->hy_hi.as<uint64_t>() : nullptr, m->err.as<int32_t>(), hint);
+            if (rc) throw ApiError(rc, last_error());
+            CUDA_CHECK(cudaMemcpyAsync(errs, m->err.p, 16, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            if (!errs[1] || m->cfg.gemm_mode < 3) break;
+            // An activation left the fp16 range (|x| > 65504; the producers saturate and raise the flag): this pass is
+            // redone with the 3xTF32 kernels, which have fp32's range -- the caller gets exact-range results either way.
+            const int mode = m->cfg.gemm_mode;
+            { const int r0 = sealbart_set_option(m, "gemm_mode", 2); if (r0) throw ApiError(r0, last_error()); }
+            m->overflow_fallbacks++;
+            rc = sealdec_generate_dx(m, fm, occ_host ? m->in_occ.as<uint32_t>() : nullptr, p, m->in_ids.as<int64_t>(),
+                                     m->in_mask.as<int64_t>(), Q, S, s, m->hy_score.as<float>(), m->hy_len.as<int32_t>(),
+                                     m->hy_tok.as<int32_t>(), m->hy_valid.as<uint8_t>(), o_lo ? m->hy_lo.as<uint64_t>() : nullptr,
+                                     o_hi ? m->hy_hi.as<uint64_t>() : nullptr, m->err.as<int32_t>(), hint);
+            const int rc2 = sealbart_set_option(m, "gemm_mode", mode);
+            if (rc) throw ApiError(rc, last_error());
+            if (rc2) throw ApiError(rc2, last_error());
+            CUDA_CHECK(cudaMemcpyAsync(errs, m->err.p, 16, cudaMemcpyDeviceToHost, s));
+            CUDA_CHECK(cudaStreamSynchronize(s));
+            break;
+        }
         CUDA_CHECK(cudaMemcpyAsync(o_score, m->hy_score.p, Q * H * 4, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaMemcpyAsync(o_len, m->hy_len.p, Q * H * 4, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaMemcpyAsync(o_tok, m->hy_tok.p, Q * H * T * 4, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaMemcpyAsync(o_valid, m->hy_valid.p, Q * H, cudaMemcpyDeviceToHost, s));
         if (o_lo) CUDA_CHECK(cudaMemcpyAsync(o_lo, m->hy_lo.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
         if (o_hi) CUDA_CHECK(cudaMemcpyAsync(o_hi, m->hy_hi.p, Q * H * 8, cudaMemcpyDeviceToHost, s));
-        int32_t errs[2] = {0, 0};
-        CUDA_CHECK(cudaMemcpyAsync(errs, m->err.p, 8, cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        const int32_t err = errs[0];
-        if (errs[1]) throw ApiError(SEALFM_EINVAL, "fp16 range exceeded in the 3xFP16 GEMM path (|x| > 65504); use gemm_mode 2 (3xTF32)");
-        if (err) throw ApiError(SEALFM_EINVAL, "beam: fewer than num_beams non-EOS candidates (seal/beam_search.py:687-690)");
+        if (errs[2]) throw ApiError(SEALFM_EINVAL, "internal: source-token count mismatch");
+        if (errs[0]) throw ApiError(SEALFM_EINVAL, "beam: fewer than num_beams non-EOS candidates (seal/beam_search.py:687-690)");
     });
 }
 
@@ -945,6 +1161,7 @@ int sealdec_debug_step_logits(sealbart_t* m, const int64_t* ids, const int64_t* 
         const int T = (int)t;
         const Dims D = make_dims(m, Q, S, B, T);
         ensure_workspace(m, D);
+        m->ovf = m->err.as<int>() + 1;
         Buf d_ids, d_mask;
         d_ids.ensure(Q * S * 8); d_mask.ensure(Q * S * 8); m->dbg_ids.ensure(D.R * t * 8);
         struct Rel { Buf *a, *b; ~Rel() { a->release(); b->release(); } } rel{&d_ids, &d_mask};
@@ -981,6 +1198,7 @@ int sealdec_teacher_forced(sealbart_t* m, const int64_t* ids, const int64_t* mas
         Dims D = make_dims(m, Q, S, 1, (int)T);
         D.R = std::min<int64_t>(N, kChunk);
         ensure_workspace(m, D);
+        m->ovf = m->err.as<int>() + 1;
         cudaStream_t s = nullptr;
         Buf d_ids, d_mask, d_dec, d_gq, d_gs, d_out, d_full;
         struct Rel { std::vector<Buf*> v; ~Rel() { for (auto b : v) b->release(); } } rel{{&d_ids, &d_mask, &d_dec, &d_gq, &d_gs, &d_out, &d_full}};
@@ -1047,7 +1265,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         CUDA_CHECK(cudaMemcpy(dW.p, W, (size_t)N * K * 4, cudaMemcpyHostToDevice));
         if (bias) CUDA_CHECK(cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
         Lin l; l.w = dW.as<float>(); l.b = bias ? dB.as<float>() : nullptr; l.out = N; l.in = K;
-        fake.err.ensure(8); CUDA_CHECK(cudaMemset(fake.err.p, 0, 8));
+        fake.err.ensure(16); CUDA_CHECK(cudaMemset(fake.err.p, 0, 16)); fake.ovf = fake.err.as<int>() + 1;
         if (mode == 1 || mode == 2) {
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();

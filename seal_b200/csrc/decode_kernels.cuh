@@ -16,7 +16,7 @@ constexpr int kSelThreads = 512;
 constexpr int kSelBuf = 8192;          // candidate staging buffer (entries)
 constexpr int kSelMaxK = 64;           // 2*num_beams <= 64
 constexpr int kSelMaxBeams = 32;
-constexpr int kMaxLen = 32;            // max_length <= 32 (SEAL: 10 body, 15 title)
+constexpr int kMaxLen = 128;           // max_length <= 128 (SEAL: 10 body, 15 title, README.md:209-216 uses 100)
 
 struct StepCfg {
     int32_t num_beams, K;              // K = 2*num_beams

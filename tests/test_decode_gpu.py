@@ -295,3 +295,124 @@ def test_index_based_logits_processor_vs_oracle(kw):
         assert torch.equal(torch.isinf(exp), torch.isinf(got)), (t, kw)
         fin = ~torch.isinf(exp)
         assert torch.equal(exp[fin], got[fin])
+
+
+def test_headline_config_q1000_10M_index_vs_oracle_sample():
+    """The benchmarked configuration itself (bench.py, BASELINE.json configs[1]): 1 000 queries x beam 15 in ONE batch
+    on the 10 M-token index with BART-large -- M = 15 000-row GEMM tiles, the compact first step, the packed encoder.
+    Checked: (a) every first-step record's [lo, hi) (30 000 ranges, the 15 000 new beams among them) against the
+    compiled reference FM-index; (b) a seeded sample of 8 queries against the reference algorithm (oracle decode, HF
+    BART eager fp32 on the same GPU): same hypotheses, |dscore| <= 1e-4, SA ranges == get_range."""
+    import torch
+    from oracle.decode_oracle import make_bart, fm_index_generate_oracle
+    from oracle.fm_oracle import OracleIndex, RefFM, PortFM, ref_available
+    from seal_b200.beam_search import SealBartEngine, generate_records, records_to_output
+    from seal_b200.cpp_modules.fm_index import FMIndex as RawFM
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import make_corpus, make_queries, corpus_symbols
+    docs = make_corpus()
+    sym = corpus_symbols(docs)
+    index = FMIndex(); RawFM.initialize(index, sym)
+    index.beginnings = list(range(0, docs.size + 1, docs.shape[1])); index._sync_beginnings(); index.to_device(0)
+    index.occurring_distinct, index.occurring_counts = index.get_distinct_count(0, len(index))
+    ora = OracleIndex(_raw=(RefFM if ref_available() else PortFM)(sym))
+    ora.beginnings = list(index.beginnings)
+    ora.occurring_distinct, ora.occurring_counts = ora.get_distinct_count(0, len(ora))
+    assert index.occurring_distinct == ora.occurring_distinct
+    model = make_bart(seed=0)
+    eng = SealBartEngine.from_hf(model, device=0)
+    ids, am = make_queries(1000, seed=4321)
+    kw = dict(num_beams=15, min_length=10, max_length=10, length_penalty=0.0)
+    rec = generate_records(eng, index, ids, am, forced_bos_token_id=None, **kw)
+    # (a) first-step records
+    K = 30
+    n = 0
+    for q in range(1000):
+        for h in range(K):
+            if rec["valid"][q, h] == 1:
+                toks = rec["tokens"][q, h, :rec["lens"][q, h]].tolist()
+                assert (int(rec["lo"][q, h]), int(rec["hi"][q, h])) == ora.get_range(toks[1:]), (q, h, toks)
+                n += 1
+    assert n >= 15000
+    # (b) sampled queries
+    sample = sorted(np.random.default_rng(7).choice(1000, size=8, replace=False).tolist())
+    model_gpu = model.to("cuda")
+    exp = fm_index_generate_oracle(model_gpu, ora, torch.tensor(ids[sample]).cuda(), torch.tensor(am[sample]).cuda(), use_cache=True, **kw)
+    got_all = records_to_output({k: v[sample] for k, v in rec.items() if v is not None}, 0.0)
+    worst = compare_generate(got_all, exp, ora)
+    for i, q in enumerate(sample):
+        for h in range(rec["scores"].shape[1]):
+            if rec["valid"][q, h] == 1:
+                toks = rec["tokens"][q, h, :rec["lens"][q, h]].tolist()
+                assert (int(rec["lo"][q, h]), int(rec["hi"][q, h])) == ora.get_range(toks[1:])
+    print(f"headline config: {n} first-step ranges exact; sample {sample}: worst |dscore| = {worst:.3e}")
+
+
+def test_device_records_graph_replay_and_host_api_agree():
+    """generate_records_device (sealdec_generate_dx): the 1st call of a shape runs eagerly, the 2nd is captured into a
+    CUDA graph, later ones replay it -- all must give the records of the host-buffer API bit for bit."""
+    import torch
+    from seal_b200._lib import lib
+    from seal_b200.beam_search import SealBartEngine, generate_records, generate_records_device
+    docs, ora, idx, model = tiny_setup()
+    eng = SealBartEngine.from_hf(model, device=0)
+    rng = np.random.default_rng(31)
+    ids, am = make_inputs(rng, Q=5, S=12, vocab=2000)
+    kw = dict(num_beams=4, min_length=6, max_length=6, length_penalty=0.0)
+    host = generate_records(eng, idx, ids.numpy(), am.numpy(), **kw)
+    ids_d = ids.cuda(); am_d = am.cuda()
+    out = None
+    used = []
+    for it in range(4):
+        out = generate_records_device(eng, idx, ids_d, am_d, out=out, src_tokens=int(am.sum()), **kw)
+        torch.cuda.synchronize()
+        used.append(int(lib.sealbart_get_stat(eng._h, b"last_used_graph")))
+        got = out.host()
+        assert not got["errors"].any()
+        for k in ("scores", "lens", "tokens", "valid", "lo", "hi"):
+            assert np.array_equal(got[k], host[k]), (it, k)
+    assert used[-1] == 1 and used[0] == 0, used
+    # a wrong source-token count is reported, not silently used
+    lib.sealbart_set_option(eng._h, b"cuda_graph", 0)
+    bad = generate_records_device(eng, idx, ids_d, am_d, src_tokens=int(am.sum()) - 1, **kw)
+    assert bad.host()["errors"][2] == 1
+
+
+def test_fp16_range_overflow_falls_back_to_tf32():
+    """activations beyond the fp16 range of the default 3xFP16 GEMM mode.  The host-buffer API repeats the
+    pass with the 3xTF32 kernels and still matches eager fp32; the device API raises error flag [1]."""
+    import torch
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200._lib import lib
+    from seal_b200.beam_search import SealBartEngine, fm_index_generate, generate_records_device
+    docs, ora, idx, model = tiny_setup()
+    with torch.no_grad():
+        model.model.decoder.layers[0].fc1.weight.mul_(2e6)        # fc1 outputs ~ 5e5 > 65504
+    eng = SealBartEngine.from_hf(model, device=0)
+    rng = np.random.default_rng(5)
+    ids, am = make_inputs(rng, Q=3, S=10, vocab=2000)
+    kw = dict(num_beams=4, min_length=5, max_length=5, length_penalty=0.0)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(eng, idx, ids, am, keep_history=True, **kw)
+    assert int(lib.sealbart_get_stat(eng._h, b"overflow_fallbacks")) >= 1
+    worst = compare_generate(got, exp, ora, tol=2e-4)
+    print(f"overflow fallback: worst |dscore| = {worst:.3e}")
+    out = generate_records_device(eng, idx, ids.cuda(), am.cuda(), **kw)
+    assert out.host()["errors"][1] == 1
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_beams=3, min_length=0, max_length=40, length_penalty=1.0, disable_fm_index=True),
+    dict(num_beams=4, min_length=0, max_length=36, length_penalty=0.0),
+])
+def test_fm_index_generate_beyond_32_positions(kw):
+    """max_length > 32 (README.md:209-216 decodes with max_length=100): the long self-attention kernel."""
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200.beam_search import fm_index_generate
+    docs, ora, idx, model = tiny_setup(n_docs=400, doc_len=60)
+    rng = np.random.default_rng(17)
+    ids, am = make_inputs(rng, Q=2, S=10, vocab=2000)
+    exp = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
+    worst = compare_generate(got, exp, ora, tol=2e-4)
+    print(f"{kw}: worst |dscore| = {worst:.3e}")

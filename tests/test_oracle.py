@@ -107,3 +107,24 @@ def test_decode_oracle_reproduces_reference_decode_outputs(case):
     for got, exp in zip(out, c["hyps"]):
         assert [list(t) for _, t, _ in got] == [t for _, t in exp]
         assert max((abs(s - e[0]) for (s, _, _), e in zip(got, exp)), default=0.0) < 1e-5
+
+
+def test_cached_stepper_equals_reforwarding_stepper():
+    """The KV-cached driver of HF BART (what the reference runs: use_cache=True + _reorder_cache, seal/beam_search.py:
+    331-332,483) returns the same hypotheses as the prefix re-forwarding one the fixtures were pinned with."""
+    import torch
+    from oracle.decode_oracle import make_bart, fm_index_generate_oracle
+    from oracle.fm_oracle import OracleIndex
+    from seal_b200.synthetic import make_corpus
+    docs = make_corpus(n_docs=300, doc_len=30, n_phrases=600, seed=3, vocab=2000)
+    ora = OracleIndex([d.tolist() for d in docs])
+    model = make_bart(seed=0, layers=2, vocab=2000, d_model=128)
+    rng = np.random.default_rng(12)
+    ids = torch.tensor(rng.integers(4, 2000, size=(3, 10)), dtype=torch.long); ids[:, 0] = 0; ids[:, -1] = 2
+    am = torch.ones_like(ids); ids[1, 7:] = 1; ids[1, 6] = 2; am[1, 7:] = 0
+    kw = dict(num_beams=5, min_length=7, max_length=7, length_penalty=0.0)
+    a = fm_index_generate_oracle(model, ora, ids, am, **kw)
+    b = fm_index_generate_oracle(model, ora, ids, am, use_cache=True, **kw)
+    for qa, qb in zip(a, b):
+        assert [tuple(t) for _, t, _ in qa] == [tuple(t) for _, t, _ in qb]
+        assert all(abs(x[0] - y[0]) < 1e-5 for x, y in zip(qa, qb))

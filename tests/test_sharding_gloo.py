@@ -27,16 +27,21 @@ def fake_generate(ids, mask, H=7, T=5):
 
 def _worker(rank, world, port, n_queries, q):
     sys.path.insert(0, ROOT)
-    from seal_b200.sharding import sharded_generate
+    from seal_b200.sharding import sharded_generate, pack_host_records
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(5)
     ids = rng.integers(0, 1000, size=(n_queries, 9)); mask = (rng.random((n_queries, 9)) < 0.8).astype(np.int64)
-    out = sharded_generate(fake_generate, ids, mask)
+
+    def fill(ids_blk, mask_blk, layout):            # what the decode kernels do on the device, done on the host here
+        rec = fake_generate(ids_blk, mask_blk) if len(ids_blk) else {}
+        return torch.from_numpy(pack_host_records(rec, layout, len(ids_blk)))
+
+    out = sharded_generate(fill, ids, mask, hyps=7, max_length=5)
     if rank == 0:
         full = fake_generate(ids, mask)
         ok = all(np.array_equal(out[k], full[k]) for k in full)
-        q.put(bool(ok) and out["scores"].shape[0] == n_queries)
+        q.put(bool(ok) and out["scores"].shape[0] == n_queries and not out["errors"].any())
     else:
         assert out is None
     dist.barrier()
@@ -68,3 +73,15 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_record_layout_round_trip():
+    from seal_b200.sharding import RecordLayout, pack_host_records, merge_gathered
+    lay = RecordLayout(5, 7, 5)
+    assert lay.nbytes % 16 == 0 and all(off % 16 == 0 for off, *_ in lay.offsets.values())
+    assert lay.record_bytes == 5 * 7 * (8 + 8 + 4 + 4 + 4 * 5 + 1)
+    rng = np.random.default_rng(1)
+    ids = rng.integers(0, 1000, size=(3, 9)); mask = np.ones_like(ids)
+    rec = fake_generate(ids, mask)
+    back = merge_gathered([pack_host_records(rec, lay, 3)], lay)
+    assert all(np.array_equal(back[k], rec[k]) for k in rec) and back["scores"].shape[0] == 3
