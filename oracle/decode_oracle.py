@@ -130,6 +130,107 @@ class HypsWithMemory:
         self.beams.append((score, list(tokens), constrained))
 
 
+class HFBeamHypotheses413:
+    """transformers 4.13 `BeamHypotheses` (generation_beam_search.py), the container behind `BeamSearchScorer` that
+    fm_index_generate builds when keep_history=False (seal/beam_search.py:505-515).  transformers 4.13 is an
+    un-vendored dependency (requirements.txt:6) and the class no longer exists in the installed 5.5, so this is a
+    restatement of its PUBLISHED algorithm -- PARITY UNPINNED for this class and `HFBeamSearchScorer413` (no
+    reference-run fixture can be produced here); everything else on the path stays pinned."""
+
+    def __init__(self, num_beams, length_penalty, early_stopping):
+        self.length_penalty = length_penalty
+        self.early_stopping = early_stopping
+        self.num_beams = num_beams
+        self.beams = []
+        self.worst_score = 1e9
+
+    def __len__(self):
+        return len(self.beams)
+
+    def add(self, hyp, sum_logprobs):
+        score = sum_logprobs / (len(hyp) ** self.length_penalty)
+        if len(self) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, list(hyp)))
+            if len(self) > self.num_beams:
+                sorted_next_scores = sorted([(s, idx) for idx, (s, _) in enumerate(self.beams)])
+                del self.beams[sorted_next_scores[0][1]]
+                self.worst_score = sorted_next_scores[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs, cur_len):
+        if len(self) < self.num_beams:
+            return False
+        if self.early_stopping:
+            return True
+        return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty
+
+
+class HFBeamSearchScorer413:
+    """transformers 4.13 `BeamSearchScorer.process / finalize` for one beam group (see HFBeamHypotheses413 for the
+    parity status).  `process` returns (scores, tokens, indices) of the next beams as flat lists."""
+
+    def __init__(self, batch_size, num_beams, length_penalty, do_early_stopping=False, num_beam_hyps_to_keep=1):
+        self.num_beams = num_beams
+        self.num_beam_hyps_to_keep = num_beam_hyps_to_keep
+        self._beam_hyps = [HFBeamHypotheses413(num_beams, length_penalty, do_early_stopping) for _ in range(batch_size)]
+        self._done = [False] * batch_size
+
+    @property
+    def is_done(self):
+        return all(self._done)
+
+    def process(self, input_ids, next_scores, next_tokens, next_indices, pad_token_id, eos_token_id):
+        cur_len = input_ids.shape[-1]
+        B = self.num_beams
+        nb_scores, nb_tokens, nb_idx = [], [], []
+        for b, hyp in enumerate(self._beam_hyps):
+            if self._done[b]:                                   # pad the batch
+                nb_scores += [0.0] * B; nb_tokens += [pad_token_id] * B; nb_idx += [0] * B
+                continue
+            beam_idx = 0
+            sc, tk, ix = [], [], []
+            for rank, (tok, s, bi) in enumerate(zip(next_tokens[b].tolist(), next_scores[b].tolist(), next_indices[b].tolist())):
+                bbi = b * B + bi
+                if eos_token_id is not None and tok == eos_token_id:
+                    if rank >= B:                               # not among the top num_beams: never added
+                        continue
+                    hyp.add(input_ids[bbi].tolist(), s)
+                else:
+                    sc.append(s); tk.append(tok); ix.append(bbi)
+                    beam_idx += 1
+                if beam_idx == B:
+                    break
+            if beam_idx < B:
+                raise ValueError(f"At most {B} tokens in {next_tokens[b]} can be equal to `eos_token_id: {eos_token_id}`. "
+                                 "Make sure {next_tokens[batch_idx]} are corrected.")
+            nb_scores += sc; nb_tokens += tk; nb_idx += ix
+            self._done[b] = self._done[b] or hyp.is_done(max(next_scores[b].tolist()), cur_len)
+        return nb_scores, nb_tokens, nb_idx
+
+    def finalize(self, input_ids, final_beam_scores, max_length, pad_token_id, eos_token_id):
+        B = self.num_beams
+        for b, hyp in enumerate(self._beam_hyps):
+            if self._done[b]:
+                continue
+            for beam_id in range(B):
+                hyp.add(input_ids[b * B + beam_id].tolist(), float(final_beam_scores[b * B + beam_id]))
+        best, best_scores = [], []
+        for hyp in self._beam_hyps:
+            sorted_hyps = sorted(hyp.beams, key=lambda x: x[0])
+            for _ in range(self.num_beam_hyps_to_keep):
+                s, t = sorted_hyps.pop()
+                best.append(t); best_scores.append(s)
+        lens = [len(t) for t in best]
+        sent_max_len = min(max(lens) + 1, max_length)
+        decoded = torch.full((len(best), sent_max_len), pad_token_id, dtype=torch.long)
+        for i, t in enumerate(best):
+            decoded[i, :lens[i]] = torch.tensor(t, dtype=torch.long)
+            if lens[i] < max_length:
+                decoded[i, lens[i]] = eos_token_id
+        return decoded, torch.tensor(best_scores, dtype=torch.float32)
+
+
 def constrained_beam_search_oracle(
         step_logits: Callable[[torch.Tensor], torch.Tensor],
         batch_size: int,
@@ -150,7 +251,9 @@ def constrained_beam_search_oracle(
         disable_fm_index: bool = False,
         processors: Sequence[str] = ("min_length", "forced_bos", "forced_eos", "inf_nan"),
         reorder: Optional[Callable[[torch.Tensor], None]] = None,
-        trace: Optional[list] = None):
+        trace: Optional[list] = None,
+        keep_history: bool = True,
+        transformers_output: bool = False):
     """fm_index_generate (:391-557, keep_history=True, diverse_bs_groups=1, sample=False, topk=0)
     + constrained_beam_search (:143-389) + BeamSearchScorerWithMemory (:559-735).
 
@@ -166,6 +269,10 @@ def constrained_beam_search_oracle(
                                               always_allow_eos=always_allow_eos,
                                               forced_bos_token_id=forced_bos_token_id)
     hyps = [HypsWithMemory(length_penalty, max_length) for _ in range(batch_size)]   # :493-503
+    hf_scorer = None
+    if not keep_history:                                                          # :505-515
+        hf_scorer = HFBeamSearchScorer413(batch_size, num_beams, length_penalty, do_early_stopping=False,
+                                          num_beam_hyps_to_keep=num_beams)
     R = batch_size * num_beams
     input_ids = torch.full((R, 1), decoder_start_token_id, dtype=torch.long)      # :485-489, :517-521
     beam_scores = torch.zeros((batch_size, num_beams), dtype=torch.float)         # :214-216
@@ -201,8 +308,18 @@ def constrained_beam_search_oracle(
             trace.append({"input_ids": input_ids.clone(), "beam_scores": beam_scores.clone(),
                           "top_scores": top_s.clone(), "top_constrained": top_c.clone(),
                           "top_tokens": next_tokens.clone(), "top_beams": next_indices.clone()})
-        # BeamSearchScorerWithMemory.process (:614-703)
         cur_len = input_ids.shape[-1]
+        if hf_scorer is not None:                                                 # BeamSearchScorer.process (transformers 4.13)
+            sc_l, tk_l, ix_l = hf_scorer.process(input_ids, top_s, next_tokens, next_indices, pad_token_id, eos_token_id)
+            beam_scores = torch.tensor(sc_l, dtype=torch.float)
+            beam_idx_flat = torch.tensor(ix_l, dtype=torch.long)
+            input_ids = torch.cat([input_ids[beam_idx_flat, :], torch.tensor(tk_l, dtype=torch.long).view(-1, 1)], dim=-1)
+            if reorder is not None:
+                reorder(beam_idx_flat)
+            if hf_scorer.is_done or input_ids.shape[-1] >= max_length:            # :340
+                break
+            continue
+        # BeamSearchScorerWithMemory.process (:614-703)
         nb_scores = torch.zeros((batch_size, num_beams)); nb_tokens = torch.zeros((batch_size, num_beams), dtype=torch.long)
         nb_idx = torch.zeros((batch_size, num_beams), dtype=torch.long)
         for b in range(batch_size):
@@ -229,6 +346,14 @@ def constrained_beam_search_oracle(
             reorder(beam_idx_flat)                                                # :331-332
         if cur_len + 0 >= max_length or input_ids.shape[-1] >= max_length:        # :340, :757-758, MaxLengthCriteria
             break
+    if hf_scorer is not None:
+        sequences, seq_scores = hf_scorer.finalize(input_ids, beam_scores, max_length, pad_token_id, eos_token_id)   # :342-350
+        if transformers_output:
+            return sequences                                                      # :388 (return_dict_in_generate is False)
+        return [[(s * (len(t) ** length_penalty), t, float("nan")) for (s, t) in h.beams if s > NEG_INF]
+                for h in hf_scorer._beam_hyps]                                    # :555
+    if trace is not None:
+        trace.append({"final_input_ids": input_ids.clone(), "final_beam_scores": beam_scores.clone()})
     for b in range(batch_size):                                                   # finalize :705-725
         for beam_id in range(num_beams):
             bbi = b * num_beams + beam_id
@@ -319,7 +444,7 @@ def fm_index_generate_oracle(model, index, input_ids, attention_mask, min_length
                              length_penalty=1.0, num_beams=3, eos_token_id=None, force_decoding_from=None,
                              always_allow_eos=False, disable_fm_index=False, stop_at_count=0,
                              processors=("min_length", "forced_bos", "forced_eos", "inf_nan"), trace=None,
-                             use_cache=False, **kw):
+                             use_cache=False, keep_history=True, transformers_output=False, **kw):
     """seal/beam_search.py:391-557 (keep_history=True path) on an HF BART model.  use_cache=True drives the decoder
     with its KV cache like the reference does (baseline timing); the default re-forwards the prefix (simplest exact form)."""
     cfg = model.config
@@ -332,4 +457,4 @@ def fm_index_generate_oracle(model, index, input_ids, attention_mask, min_length
         model_eos_token_id=cfg.eos_token_id, forced_eos_token_id=cfg.forced_eos_token_id,
         forced_bos_token_id=forced_bos, force_decoding_from=force_decoding_from, stop_at_count=stop_at_count,
         always_allow_eos=always_allow_eos, disable_fm_index=disable_fm_index, processors=processors, trace=trace,
-        reorder=stepper.reorder if use_cache else None)
+        reorder=stepper.reorder if use_cache else None, keep_history=keep_history, transformers_output=transformers_output)

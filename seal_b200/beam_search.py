@@ -3,10 +3,11 @@
 * ``IndexBasedLogitsProcessor`` — same constructor, attributes and HF ``LogitsProcessor`` protocol
   (``__call__(input_ids, scores) -> scores + mask``, beam_search.py:33-140); the FM-index work and
   the mask run as CUDA kernels on the tensors' device, no ``.tolist()`` / H2D round trips.
-* ``fm_index_generate`` — same signature and return value (beam_search.py:391-557) for the path
-  SEALSearcher uses (``keep_history=True``, one beam group, no sampling): encoder, every decoder
-  step, log-softmax, processors, FM-index constraint, top-k and BeamSearchScorerWithMemory all run
-  inside libsealb200.so.
+* ``fm_index_generate`` — same signature and return value (beam_search.py:391-557), one beam group, no
+  sampling: encoder, every decoder step, log-softmax, processors, FM-index constraint, top-k and
+  BeamSearchScorerWithMemory all run inside libsealb200.so.  ``keep_history=True`` is the path SEALSearcher
+  uses; ``keep_history=False`` (transformers' stock BeamSearchScorer, the signature's default) and
+  ``transformers_output=True`` run the same kernels and replay the stock scorer over the per-step records.
 * ``SealBartEngine`` — device copy of an HF ``BartForConditionalGeneration``'s weights.
 
 No CPU path: CPU tensors are rejected.
@@ -384,6 +385,75 @@ def records_to_output(rec, length_penalty):
     return out
 
 
+def _replay_beam_search_scorer(rec, num_beams, length_penalty, eos_token_id, pad_token_id, max_length):
+    """keep_history=False (seal/beam_search.py:505-515): the reference hands the loop transformers 4.13's stock
+    `BeamSearchScorer` instead of BeamSearchScorerWithMemory.  Both choose the next beams the same way (the first
+    num_beams non-EOS candidates of the top 2*num_beams), so the beams evolve identically until a query is `done`,
+    after which the stock scorer freezes it (pads) and `finalize` skips it.  The device path therefore runs the very
+    same kernels, and the stock scorer's bookkeeping -- BeamHypotheses.add / worst_score / is_done, process's
+    "EOS only if ranked inside the top num_beams", finalize's best-num_beams selection with an appended EOS -- is
+    replayed here, on the host, over the per-step candidate records (a few thousand scalar operations per query).
+    Returns (beams per query [(score, tokens)] in BeamHypotheses order, sequences int64 [Q*num_beams, L],
+    sequence_scores float32 [Q*num_beams]).  transformers 4.13 is not vendored: restated from its published algorithm."""
+    scores, lens, toks = rec["scores"], rec["lens"], rec["tokens"]
+    Q, H = scores.shape
+    B, K = num_beams, 2 * num_beams
+    n_steps = (H - B) // K
+    all_beams, best, best_scores = [], [], []
+    for q in range(Q):
+        beams = []; worst = 1e9; done = False
+
+        def add(tokens, sum_logprobs):
+            nonlocal worst
+            score = sum_logprobs / (len(tokens) ** length_penalty)
+            if len(beams) < B or score > worst:
+                beams.append((score, tokens))
+                if len(beams) > B:
+                    order = sorted((sc, i) for i, (sc, _) in enumerate(beams))
+                    del beams[order[0][1]]
+                    worst = order[1][0]
+                else:
+                    worst = min(score, worst)
+
+        for st in range(n_steps):
+            if done:
+                break
+            cur_len = st + 1
+            base = st * K
+            cand_s = scores[q, base:base + K].tolist()
+            nb = 0
+            for rank in range(K):
+                h = base + rank
+                tok = int(toks[q, h, cur_len])
+                if tok == eos_token_id:
+                    if rank < B:
+                        add(toks[q, h, :cur_len].tolist(), cand_s[rank])
+                else:
+                    nb += 1
+                if nb == B:
+                    break
+            if nb < B:
+                raise ValueError(f"At most {B} tokens can be equal to `eos_token_id: {eos_token_id}`.")
+            if len(beams) >= B:
+                done = worst >= max(cand_s) / cur_len ** length_penalty
+        if not done:
+            fb = n_steps * K
+            for j in range(B):
+                add(toks[q, fb + j, :lens[q, fb + j]].tolist(), float(scores[q, fb + j]))
+        all_beams.append(list(beams))
+        order = sorted(beams, key=lambda x: x[0])
+        for _ in range(B):
+            sc, t = order.pop()
+            best.append(t); best_scores.append(sc)
+    L = min(max(len(t) for t in best) + 1, max_length) if best else 0
+    seq = np.full((len(best), L), pad_token_id, dtype=np.int64)
+    for i, t in enumerate(best):
+        seq[i, :len(t)] = t
+        if len(t) < max_length:
+            seq[i, len(t)] = eos_token_id
+    return all_beams, seq, np.asarray(best_scores, dtype=np.float32)
+
+
 def fm_index_generate(model, index: FMIndex, input_ids, attention_mask, min_length: int = 3, max_length: int = 25,
                       length_penalty: float = 1.0, num_beams: int = 3, diverse_bs_groups: int = 1,
                       diverse_bs_penalty: float = 0.0, eos_token_id: Optional[int] = None,
@@ -392,14 +462,42 @@ def fm_index_generate(model, index: FMIndex, input_ids, attention_mask, min_leng
                       stop_at_count: int = 0, topk: int = 0, transformers_output: bool = False, **kwargs):
     """beam_search.py:391-557.  `model` is an HF BartForConditionalGeneration (its weights are
     mirrored on the GPU once and cached) or a SealBartEngine."""
-    if not keep_history:
-        raise NotImplementedError("seal_b200 implements the keep_history=True path SEALSearcher uses "
-                                  "(seal/retrieval.py:70-83,162-176,223-236)")
-    if diverse_bs_groups != 1 or sample or topk or transformers_output:
-        raise NotImplementedError("diverse beam groups / sampling / top-k warping / HF output objects are outside "
-                                  "the constrained-decoding hot path")
+    if diverse_bs_groups != 1 or sample or topk:
+        raise NotImplementedError("diverse beam groups / sampling / top-k warping are outside the constrained-decoding hot path")
     forced_bos = kwargs.pop("forced_bos_token_id", "config")                     # :415-418
-    rec = generate_records(model, index, input_ids, attention_mask, min_length, max_length, length_penalty,
-                           num_beams, eos_token_id, force_decoding_from, always_allow_eos, disable_fm_index,
-                           stop_at_count, forced_bos, want_ranges=False)
-    return records_to_output(rec, length_penalty)
+    torch = _torch()
+    if keep_history:
+        rec = generate_records(model, index, input_ids, attention_mask, min_length, max_length, length_penalty,
+                               num_beams, eos_token_id, force_decoding_from, always_allow_eos, disable_fm_index,
+                               stop_at_count, forced_bos, want_ranges=False)
+        if transformers_output:
+            # BeamSearchScorerWithMemory.finalize returns an UNINITIALISED [Q*num_beams, 3] tensor as `sequences`
+            # (:727); zeros of that shape here
+            return torch.zeros((rec["scores"].shape[0] * num_beams, 3), dtype=torch.long,
+                               device=input_ids.device if hasattr(input_ids, "device") else "cpu")
+        return records_to_output(rec, length_penalty)
+    # ---- keep_history=False: transformers' stock BeamSearchScorer (:505-515), the reference's default --------------
+    eng = _engine_for(model)
+    cfg = eng.config
+    eos = cfg.eos_token_id if eos_token_id is None else eos_token_id
+    dev = torch.device("cuda", eng.device)
+    ids_np = np.ascontiguousarray(np.asarray(input_ids.cpu() if hasattr(input_ids, "cpu") else input_ids, dtype=np.int64))
+    am_np = np.ascontiguousarray(np.asarray(attention_mask.cpu() if hasattr(attention_mask, "cpu") else attention_mask, dtype=np.int64))
+    out = generate_records_device(eng, index, torch.from_numpy(ids_np).to(dev), torch.from_numpy(am_np).to(dev), min_length,
+                                  max_length, length_penalty, num_beams, eos_token_id, force_decoding_from, always_allow_eos,
+                                  disable_fm_index, stop_at_count, forced_bos, src_tokens=-2)
+    rec = out.host()
+    if rec["errors"][1] and eng.gemm_mode >= 3:        # fp16 range exceeded: redo with the 3xTF32 kernels (sealdec.h)
+        check(lib.sealbart_set_option(eng._h, b"gemm_mode", 2))
+        try:
+            rec = generate_records_device(eng, index, torch.from_numpy(ids_np).to(dev), torch.from_numpy(am_np).to(dev), min_length,
+                                          max_length, length_penalty, num_beams, eos_token_id, force_decoding_from, always_allow_eos,
+                                          disable_fm_index, stop_at_count, forced_bos, src_tokens=-2).host()
+        finally:
+            check(lib.sealbart_set_option(eng._h, b"gemm_mode", eng.gemm_mode))
+    # the device's "fewer than num_beams non-EOS candidates" flag also fires for queries the stock scorer had already
+    # frozen; the replay re-derives the condition per query and step and raises exactly where the reference does
+    beams, seq, _ = _replay_beam_search_scorer(rec, num_beams, length_penalty, eos, cfg.pad_token_id, int(max_length))
+    if transformers_output:
+        return torch.from_numpy(seq).to(input_ids.device if hasattr(input_ids, "device") else "cpu")     # :388
+    return [[(sc * (len(t) ** length_penalty), t) for sc, t in b if sc > float("-inf")] for b in beams]    # :555

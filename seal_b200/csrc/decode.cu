@@ -75,6 +75,7 @@ struct sealbart {
     Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
     Buf ex_hi, ex_lo, eattn_hi, eattn_lo, effn_hi, effn_lo, dx_hi, dx_lo, dattn_hi, dattn_lo, dffn_hi, dffn_lo;   // TF32 splits (gemm_mode 1)
     Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
+    Buf st_rowmax, st_rowls, st_rule, st_cval, st_cidx, st_ccnt, st_wide;     // scratch between the kernels of a step
     Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo, splitk;
     std::vector<void*> split_allocs;
     int64_t launches = 0;
@@ -478,6 +479,9 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_scores.ensure(2 * D.R * 4); m->st_tokens.ensure(2 * D.R * D.T * 4);
     m->st_lo.ensure(2 * D.R * 8); m->st_hi.ensure(2 * D.R * 8); m->st_pw.ensure(2 * D.R * 8);
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
+    m->st_rowmax.ensure(D.R * 4); m->st_rowls.ensure(D.R * 4); m->st_rule.ensure(D.R);
+    m->st_cval.ensure((size_t)D.R * 2 * D.B * 4); m->st_cidx.ensure((size_t)D.R * 2 * D.B * 4); m->st_ccnt.ensure(D.R * 4);
+    m->st_wide.ensure((D.R + 2) * 8);
     if (m->cfg.gemm_mode >= 1) {
         m->ex_hi.ensure(Tk * D.d * 4); m->ex_lo.ensure(Tk * D.d * 4);
         m->eattn_hi.ensure(Tk * D.d * 4); m->eattn_lo.ensure(Tk * D.d * 4);
@@ -701,7 +705,8 @@ void sealbart_free(sealbart_t* m) {
     if (m->lm_head_given) cudaFree(m->lm_head);
     for (Buf* b : {&m->enc_tok, &m->enc_mask, &m->src_off, &m->ex, &m->eqkv, &m->eattn, &m->etmp, &m->effn, &m->ckv, &m->dx, &m->dqkv,
                    &m->dattn, &m->dtmp, &m->dcq, &m->dffn, &m->logits, &m->kc, &m->vc, &m->st_scores, &m->st_tokens,
-                   &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->hy_score, &m->hy_len, &m->hy_tok,
+                   &m->st_lo, &m->st_hi, &m->st_pw, &m->st_anc, &m->st_mask, &m->st_rowmax, &m->st_rowls, &m->st_rule, &m->st_cval,
+                   &m->st_cidx, &m->st_ccnt, &m->st_wide, &m->hy_score, &m->hy_len, &m->hy_tok,
                    &m->hy_valid, &m->hy_lo, &m->hy_hi, &m->err, &m->dbg_ids, &m->force_syms, &m->a_hi, &m->a_lo, &m->ex_hi, &m->ex_lo,
                    &m->eattn_hi, &m->eattn_lo, &m->effn_hi, &m->effn_lo, &m->dx_hi, &m->dx_lo, &m->dattn_hi, &m->dattn_lo,
                    &m->dffn_hi, &m->dffn_lo, &m->splitk})
@@ -839,7 +844,11 @@ void generate_enqueue(Ctx& cx, const Dims& D, const GenArgs& a, const FmView& vi
     c.stop_at_count = p->stop_at_count; c.always_allow_eos = p->always_allow_eos; c.disable_fm_index = p->disable_fm_index;
     c.remove_invalid_values = p->remove_invalid_values; c.shift = p->shift; c.T = T; c.mask_words = D.W;
     c.hyps_per_query = sealdec_hyps_per_query(p);
-    CUDA_CHECK(cudaFuncSetAttribute(select_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SelShared)));
+    using RowsFirst = SelSharedT<8192>; using RowsLater = SelSharedT<4096>;
+    CUDA_CHECK(cudaFuncSetAttribute(topk_rows_kernel<512, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsFirst)));
+    CUDA_CHECK(cudaFuncSetAttribute(topk_rows_kernel<256, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RowsLater)));
+    RowScratch rs{m->st_rowmax.as<float>(), m->st_rowls.as<float>(), m->st_rule.as<uint8_t>(),
+                  m->st_cval.as<float>(), m->st_cidx.as<int32_t>(), m->st_ccnt.as<int32_t>()};
     int cur = 0;
     for (int step = 0; step + 1 < T; ++step) {
         const int cur_len = step + 1;
@@ -875,8 +884,22 @@ void generate_enqueue(Ctx& cx, const Dims& D, const GenArgs& a, const FmView& vi
         st.occurring_mask = a.occ_d; st.logits = m->logits.as<float>();
         st.hyp_score = a.o_score; st.hyp_len = a.o_len; st.hyp_tokens = a.o_tok; st.hyp_valid = a.o_valid;
         st.hyp_lo = a.o_lo; st.hyp_hi = a.o_hi; st.error_flag = a.err_d;
-        select_step_kernel<0><<<(unsigned)Q, kSelThreads, sizeof(SelShared), cx.s>>>(view, c, st);
+        // first step: beams 1.. carry -1e9 and are pruned exactly inside one CTA per query; afterwards one CTA per row
+        if (cur_len == 1) {
+            topk_rows_kernel<512, 8192><<<(unsigned)Q, 512, sizeof(RowsFirst), cx.s>>>(c, st, rs, 1, B);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            select_merge_kernel<<<(unsigned)Q, kMergeThreads, 0, cx.s>>>(view, c, st, rs, 1);
+        } else {
+            topk_rows_kernel<256, 4096><<<(unsigned)R, 256, sizeof(RowsLater), cx.s>>>(c, st, rs, B, 1);
+            CUDA_CHECK(cudaGetLastError()); m->launches++;
+            select_merge_kernel<<<(unsigned)Q, kMergeThreads, 0, cx.s>>>(view, c, st, rs, B);
+        }
         CUDA_CHECK(cudaGetLastError()); m->launches++;
+        if (c.expand_next && !p->disable_fm_index) {           // successor sets of the new beams -> next step's masks (:107)
+            launch_expand_masks(view, cx.s, (uint64_t)R, lo[cur ^ 1], hi[cur ^ 1], mk[cur ^ 1], (uint32_t)D.W, (uint32_t)D.V,
+                                (uint32_t)p->shift, m->st_wide.as<unsigned long long>());
+            m->launches += 2;
+        }
         mark();
         cur ^= 1;
     }

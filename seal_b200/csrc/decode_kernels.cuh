@@ -1,19 +1,17 @@
 // Constrained beam-search step on the device: full-vocabulary log-softmax, HF logits processors,
-// FM-index mask, top-(2*beam) over the constrained scores, BeamSearchScorerWithMemory bookkeeping,
-// LF-mapping of the surviving beams and expansion of their successor sets — ONE kernel per step,
-// one CTA per query.  Replaces seal/beam_search.py:244-332 + :614-703 and the CPU FM-index work of
-// :62-140 without a single host synchronisation.
+// FM-index mask and per-row top-(2*beam) (topk_rows_kernel, one CTA per row), then per query the merge,
+// BeamSearchScorerWithMemory bookkeeping and LF-mapping of the surviving beams (select_merge_kernel); the
+// successor sets of the new beams are expanded by the FM-index kernels (fm_kernels.cu) over all rows.
+// Replaces seal/beam_search.py:244-332 + :614-703 and the CPU FM-index work of :62-140 without a single
+// host synchronisation.
 #pragma once
 #include "fm_device.cuh"
-#include "fm_expand.cuh"
 
 #include <cfloat>
 #include <cstdint>
 
 namespace sealb200 {
 
-constexpr int kSelThreads = 512;
-constexpr int kSelBuf = 8192;          // candidate staging buffer (entries)
 constexpr int kSelMaxK = 64;           // 2*num_beams <= 64
 constexpr int kSelMaxBeams = 32;
 constexpr int kMaxLen = 128;           // max_length <= 128 (SEAL: 10 body, 15 title, README.md:209-216 uses 100)
@@ -90,26 +88,24 @@ __device__ __forceinline__ bool cand_better(float sa, int ia, float sb, int ib) 
     return sa > sb || (sa == sb && ia < ib);
 }
 
-struct SelShared {
-    float cval[kSelBuf + kSelMaxK];
-    int cidx[kSelBuf + kSelMaxK];
+// Candidate staging + running top-K of one CTA of topk_rows_kernel.
+template <int BUF>
+struct SelSharedT {
+    static constexpr int kBuf = BUF;
+    float cval[BUF + kSelMaxK];
+    int cidx[BUF + kSelMaxK];
     float tval[kSelMaxK];
     int tidx[kSelMaxK];
-    uint8_t tvalid[kSelMaxK];
-    float row_max[kSelMaxBeams], row_logsum[kSelMaxBeams];
-    uint8_t row_rule[kSelMaxBeams];       // 0 index set, 1 only eos, 2 only pad
-    float red[kSelThreads / 32];
-    float rv[kSelThreads / 32]; int ri[kSelThreads / 32]; int rslot[kSelThreads / 32];
+    float red[32];
+    float rv[32]; int ri[32]; int rslot[32];
     int ccount, tcount, overflow;
     float thr; int thr_idx;
-    int nbeam_src[kSelMaxBeams];          // candidate index feeding each new beam
-    int n_noneos;
-    WarpFrontier frontier[kSelThreads / 32];
 };
 
 // Select the best min(K, n) of the n staged candidates (cval/cidx[0..n)) in order; result in
 // tval/tidx[0..tcount).  K rounds of block-wide arg-best.
-__device__ void sel_merge(SelShared& S, int K) {
+template <typename SH>
+__device__ void sel_merge(SH& S, int K) {
     // current top list is appended to the staging area so one pass handles both
     __syncthreads();
     int n = S.ccount;
@@ -151,18 +147,33 @@ __device__ void sel_merge(SelShared& S, int K) {
     __syncthreads();
 }
 
-template <int DUMMY = 0>
-__global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, StepCfg c, StepState st) {
+// Per-row scratch between the two kernels of a step.
+struct RowScratch {
+    float* row_max; float* row_logsum; uint8_t* row_rule;     // [R]  log-softmax statistics / index rule of every row
+    float* cand_val; int32_t* cand_idx; int32_t* cand_cnt;    // [Q * groups][K] sorted best candidates per row group, [Q * groups]
+};
+
+// ---- step kernel 1 of 2: row statistics + the best K constrained candidates of a GROUP of beams ---------------------
+// grid = Q * groups CTAs; group g of query q covers beams [g * rows_per_cta, ...).  After the first step a group is ONE
+// row (groups = num_beams): 15 000 CTAs stream the 3 GB of logits in parallel (round 1 gave a whole query -- 15 rows,
+// 3 MB -- to one CTA: 1.55 ms per step against a 0.46 ms byte floor, and 20 busy SMs at batch 20).  At the first step a
+// group is the whole query (groups = 1): beams 1.. carry -1e9 and are pruned exactly against the running K-th best.
+// Full-vocabulary log-softmax (seal/beam_search.py:251), HF processors (:255), FM-index mask (:260-262), top-2B of
+// the constrained scores restricted to the group (:302-307) -- exact: the query's top-K is the top-K of its groups' top-Ks.
+template <int THREADS, int BUF>
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : 4) topk_rows_kernel(StepCfg c, StepState st, RowScratch rs, int groups, int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    SelShared& S = *reinterpret_cast<SelShared*>(smem_raw);
+    using SH = SelSharedT<BUF>;
+    SH& S = *reinterpret_cast<SH*>(smem_raw);
     const int B = c.num_beams, K = c.K, V = c.V;
-    const int64_t qi = blockIdx.x;
+    const int64_t qi = blockIdx.x / groups;
+    const int g = blockIdx.x - (int)(qi * groups);
     const int64_t r0 = qi * B;
     const int tid = threadIdx.x;
-    if (tid == 0) { S.ccount = 0; S.tcount = 0; S.overflow = 0; S.thr = -INFINITY; S.thr_idx = 0x7fffffff; S.n_noneos = 0; }
+    if (tid == 0) { S.ccount = 0; S.tcount = 0; S.overflow = 0; S.thr = -INFINITY; S.thr_idx = 0x7fffffff; }
     __syncthreads();
-
-    for (int b = 0; b < B; ++b) {
+    const int b_end = (g + 1) * rows_per_cta < B ? (g + 1) * rows_per_cta : B;
+    for (int b = g * rows_per_cta; b < b_end; ++b) {
         const int64_t r = r0 + b;
         const float* lp = st.logits + (c.logits_shared ? qi : r) * c.ld;
         // Exact pruning: every candidate of this row scores <= beam_score (log-probs <= 0, forced tokens
@@ -175,9 +186,8 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         float mx = -INFINITY, se = 0.f;
         if (c.logits_ignored) { mx = 0.f; se = 1.f; }           // log-softmax statistics are never used (uniform branch)
         else {
-        // four 16-byte loads in flight per thread, one running-max update per 16 values (the loop is bound by
-        // load latency and instruction issue, not by HBM: profiles/r01_ncu_select_v2_raw.csv)
-        constexpr int kStride = kSelThreads * 4;
+        // four 16-byte loads in flight per thread, one running-max update per 16 values
+        constexpr int kStride = THREADS * 4;
         int v = tid * 4;
         for (; v + 3 * kStride + 3 < V; v += 4 * kStride) {
             const float4 a = *reinterpret_cast<const float4*>(lp + v);
@@ -231,7 +241,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             if (c.stop_at_count > 0 && count <= (uint64_t)c.stop_at_count) rule = 1;
             else if (ended) rule = 2;
         }
-        if (tid == 0) { S.row_max[b] = mx; S.row_logsum[b] = logsum; S.row_rule[b] = (uint8_t)rule; }
+        if (tid == 0) { rs.row_max[r] = mx; rs.row_logsum[r] = logsum; rs.row_rule[r] = (uint8_t)rule; }
         const float bs = st.beam_scores_in[r];
         // ---- stage candidates whose constrained score is finite and not below the running k-th best.
         // Fast path: one barrier-free sweep over the row's mask words (rows allow a handful of tokens
@@ -256,13 +266,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             const int flat = b * V + v;
             if (s > -INFINITY && (S.tcount < K || cand_better(s, flat, S.thr, S.thr_idx))) {
                 const int slot = atomicAdd(&S.ccount, 1);
-                if (!guarded || slot < kSelBuf) { S.cval[slot] = s; S.cidx[slot] = flat; }
+                if (!guarded || slot < BUF) { S.cval[slot] = s; S.cidx[slot] = flat; }
                 else S.overflow = 1;
             }
         };
         __syncthreads();
         const int count_before = S.ccount;
-        for (int w = tid; w < c.mask_words; w += kSelThreads) {
+        for (int w = tid; w < c.mask_words; w += THREADS) {
             uint32_t bits = row_bits(w);
             while (bits) {
                 const int bit = __ffs(bits) - 1; bits &= bits - 1;
@@ -274,12 +284,12 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         const int staged_fast = S.ccount;
         __syncthreads();
         if (!overflow) {
-            if (staged_fast > kSelBuf / 2) sel_merge(S, K);      // keep room for the next rows
+            if (staged_fast > BUF / 2) sel_merge(S, K);          // keep room for the next rows
         } else {
             if (tid == 0) { S.ccount = count_before; S.overflow = 0; }
             __syncthreads();
             if (count_before > 0) sel_merge(S, K);
-            for (int w0 = 0; w0 < c.mask_words; w0 += kSelThreads) {
+            for (int w0 = 0; w0 < c.mask_words; w0 += THREADS) {
                 const int w = w0 + tid;
                 const uint32_t bits = w < c.mask_words ? row_bits(w) : 0u;
                 for (int sub = 0; sub < 4; ++sub) {
@@ -291,23 +301,90 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
                     __syncthreads();
                     const int staged = S.ccount;                 // read between two barriers:
                     __syncthreads();                             // the branch below is uniform
-                    if (staged > kSelBuf - kSelThreads * 8) sel_merge(S, K);
+                    if (staged > BUF - THREADS * 8) sel_merge(S, K);
                 }
             }
         }
     }
     sel_merge(S, K);
+    static_assert(BUF >= THREADS * 16, "a sub-round stages up to 8 candidates per thread on top of a half-full buffer");
+    const int64_t gidx = qi * groups + g;
+    for (int k = tid; k < S.tcount; k += THREADS) { rs.cand_val[gidx * K + k] = S.tval[k]; rs.cand_idx[gidx * K + k] = S.tidx[k]; }
+    if (tid == 0) rs.cand_cnt[gidx] = S.tcount;
+}
+
+constexpr int kMergeThreads = 128;
+
+struct MergeShared {
+    float cval[kSelMaxBeams * kSelMaxK];
+    int cidx[kSelMaxBeams * kSelMaxK];
+    float tval[kSelMaxK];
+    int tidx[kSelMaxK];
+    uint8_t tvalid[kSelMaxK];
+    float rv[kMergeThreads / 32]; int ri[kMergeThreads / 32]; int rslot[kMergeThreads / 32];
+    int tcount;
+    int nbeam_src[kSelMaxBeams];          // candidate index feeding each new beam
+    int n_noneos;
+};
+
+// ---- step kernel 2 of 2, one CTA per query: merge the groups' candidate lists into the query's top-2B (:302-307),
+// -inf fill-ins, BeamSearchScorerWithMemory.process (:614-703), hypothesis records, and the LF step
+// (incremental get_range) of every record and new beam.  The successor sets of the new beams (next step's masks)
+// are expanded by the FM-index kernels right after (fm_kernels.cu launch_expand_masks), over all rows of the batch.
+__global__ void __launch_bounds__(kMergeThreads) select_merge_kernel(FmView fm, StepCfg c, StepState st, RowScratch rs, int groups) {
+    __shared__ MergeShared S;
+    const int B = c.num_beams, K = c.K, V = c.V;
+    const int64_t qi = blockIdx.x;
+    const int64_t r0 = qi * B;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    // gather the sorted lists of this query's groups
+    int n = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int cnt = rs.cand_cnt[qi * groups + g];
+        for (int k = tid; k < cnt; k += kMergeThreads) { S.cval[n + k] = rs.cand_val[(qi * groups + g) * K + k]; S.cidx[n + k] = rs.cand_idx[(qi * groups + g) * K + k]; }
+        n += cnt;
+    }
+    __syncthreads();
+    const int want = n < K ? n : K;
+    for (int round = 0; round < want; ++round) {
+        float bv = -INFINITY; int bi = 0x7fffffff; int bs = -1;
+        for (int i = tid; i < n; i += kMergeThreads) {
+            const int id = S.cidx[i];
+            if (id < 0) continue;
+            const float v = S.cval[i];
+            if (bs < 0 || cand_better(v, id, bv, bi)) { bv = v; bi = id; bs = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (os >= 0 && (bs < 0 || cand_better(ov, oi, bv, bi))) { bv = ov; bi = oi; bs = os; }
+        }
+        if (lane == 0) { S.rv[warp] = bv; S.ri[warp] = bi; S.rslot[warp] = bs; }
+        __syncthreads();
+        if (tid == 0) {
+            float v = S.rv[0]; int id = S.ri[0]; int sl = S.rslot[0];
+            for (int w = 1; w < kMergeThreads / 32; ++w)
+                if (S.rslot[w] >= 0 && (sl < 0 || cand_better(S.rv[w], S.ri[w], v, id))) { v = S.rv[w]; id = S.ri[w]; sl = S.rslot[w]; }
+            S.tval[round] = v; S.tidx[round] = id;
+            S.cidx[sl] = -1;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) S.tcount = want;
+    if (tid < kSelMaxK) S.tvalid[tid] = tid < want ? 1 : 0;
+    __syncthreads();
 
     // ---- fewer than K finite constrained candidates: fill with masked ones -------
     // torch.topk's choice among -inf ties is unspecified; ours: lowest flat index first.
-    if (tid < kSelMaxK) S.tvalid[tid] = tid < S.tcount ? 1 : 0;
-    __syncthreads();
     if (tid == 0 && S.tcount < K) {
         int have = S.tcount;
         for (int flat = 0; have < K && flat < B * V; ++flat) {
             const int b = flat / V, v = flat - b * V;
             const int64_t r = r0 + b;
-            float p = c.logits_ignored ? 0.f : (st.logits[(c.logits_shared ? qi : r) * c.ld + v] - S.row_max[b]) - S.row_logsum[b];
+            float p = c.logits_ignored ? 0.f : (st.logits[(c.logits_shared ? qi : r) * c.ld + v] - rs.row_max[r]) - rs.row_logsum[r];
             p = apply_processors(c, v, p);
             const float s = p + st.beam_scores_in[r];
             // was it a finite constrained candidate (then it is already in the list)?
@@ -316,7 +393,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             else if (c.forced_bos_token_id >= 0 && c.cur_len == 1) allowed = v == c.forced_bos_token_id;
             else {
                 const uint32_t* mrow = c.first_step_shared_mask ? st.occurring_mask : st.mask_in + r * c.mask_words;
-                const int rule = S.row_rule[b];
+                const int rule = rs.row_rule[r];
                 allowed = rule == 1 ? v == c.eos_token_id : rule == 2 ? v == c.pad_token_id : ((mrow[v >> 5] >> (v & 31)) & 1);
                 if (c.always_allow_eos && v == c.eos_token_id) allowed = true;
             }
@@ -363,9 +440,11 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
             st.hyp_lo[h] = l; st.hyp_hi[h] = r;
         }
     }
-    // ---- next beams: state of row j comes from candidate nbeam_src[j] ------------------------------
-    if (tid < B) {
-        const int j = tid;
+    // ---- next beams: state of row j comes from candidate nbeam_src[j] (threads K .. K+B-1: other warps than the
+    // record writers where possible) -------------------------------------------------------------------------------
+    const int jt = tid - (K + B <= kMergeThreads ? K : 0);
+    if (jt >= 0 && jt < B) {
+        const int j = jt;
         const int64_t nr = r0 + j;
         if (j < S.n_noneos) {
             const int k = S.nbeam_src[j];
@@ -397,35 +476,6 @@ __global__ void __launch_bounds__(kSelThreads, 2) select_step_kernel(FmView fm, 
         } else {
             st.beam_scores_out[nr] = 0.f;
             st.lo_out[nr] = 0; st.hi_out[nr] = 0; st.pw_out[nr] = 0;
-        }
-    }
-    __syncthreads();
-    // ---- successor sets of the new beams -> next step's masks (distinct_count_multi, :107) ---------
-    if (c.expand_next && !c.disable_fm_index) {
-        const int warp = tid >> 5, lane = tid & 31, nw = kSelThreads / 32;
-        for (int j = warp; j < B; j += nw) {
-            const int64_t nr = r0 + j;
-            uint32_t* row = st.mask_out + nr * c.mask_words;
-            for (int w = lane; w < c.mask_words; w += 32) row[w] = 0;
-            __syncwarp();
-            const uint64_t l = st.lo_out[nr], h = st.hi_out[nr];
-            if (h > l && h - l >= kWideRange) continue;        // wide: whole CTA below
-            MaskSink sink{row, (uint32_t)V, (uint32_t)c.shift};
-            warp_expand(fm, l, h, sink, S.frontier[warp]);
-            __syncwarp();
-        }
-        __syncthreads();
-        // wide successor sets (thousands of distinct tokens): all 512 threads expand one beam at a time;
-        // the candidate staging area is free by now and holds the block frontier
-        using SelFrontier = BlockFrontierT<1536>;
-        static_assert(sizeof(SelFrontier) <= sizeof(S.cval) + sizeof(S.cidx), "frontier must fit the staging area");
-        SelFrontier& BF = *reinterpret_cast<SelFrontier*>(S.cval);
-        for (int j = 0; j < B; ++j) {
-            const int64_t nr = r0 + j;
-            const uint64_t l = st.lo_out[nr], h = st.hi_out[nr];
-            if (!(h > l && h - l >= kWideRange)) continue;     // uniform
-            MaskSink sink{st.mask_out + nr * c.mask_words, (uint32_t)V, (uint32_t)c.shift};
-            block_expand(fm, l, h, sink, BF);
         }
     }
 }

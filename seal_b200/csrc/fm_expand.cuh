@@ -21,17 +21,74 @@ struct DenseSink {
     __device__ void operator()(uint32_t symbol, uint64_t ri, uint64_t rj) const { counts[symbol] = rj - ri; }
 };
 
+// Depth-first expansion below (level, prefix) WITHOUT a local-memory stack.  A thread only ever has to remember
+// the right sibling of the nodes on its current root-to-node path where both children exist: at most one (i, j)
+// pair per tree level.  Those live in shared memory ([level][slot], conflict-free), a 32-bit mask says which
+// levels are pending, and the prefix of a popped sibling is rebuilt from the current prefix (the ancestor at that
+// level is the left child).  The previous per-thread `Frame stk[36]` (48-byte frames in local memory) produced
+// ~6x the algorithmic traffic in the wide regime (profiles/r01_expand_kernels_ncu.csv).  The children's node-table
+// entries share one 32-byte sector and are fetched together with the rank sectors, so a level costs ONE dependent
+// memory round trip; a popped sibling re-reads its entry (once per branching node, top-of-tree entries are cache-hot).
+// Symbols are delivered in ascending order per call, like wt_int::_interval_symbols (sdsl/wt_int.hpp:108-147).
+template <typename Sink>
+__device__ __forceinline__ void expand_dfs_smem(const FmView& v, uint32_t level, uint32_t prefix, uint64_t i, uint64_t j, Sink& sink,
+                                                uint64_t* __restrict__ stk_i, uint64_t* __restrict__ stk_j, int stride, int slot) {
+    const uint32_t L = v.L;
+    uint32_t pending = 0;
+    NodeEntry e{0, 0};
+    if (level < L) e = load_node(v, (1u << level) + prefix);
+    for (;;) {
+        if (level == L) {
+            sink(prefix, i, j);
+        } else {
+            NodeEntry c0{0, 0}, c1{0, 0};
+            if (level + 1 < L) {
+                const uint32_t h = (2u << level) + 2u * prefix;
+                c0 = load_node(v, h); c1 = load_node(v, h + 1);
+            }
+            uint64_t a, b;
+            if (j == i + 1) {                                  // single position: one sector, take the bit
+                int bit;
+                a = rank1(v, e.base + i, &bit) - e.ones;
+                b = a + static_cast<uint64_t>(bit);
+            } else {
+                a = rank1(v, e.base + i) - e.ones;
+                b = rank1(v, e.base + j) - e.ones;
+            }
+            const bool has1 = b != a, has0 = (j - i) != (b - a);
+            if (has0) {
+                if (has1) { stk_i[level * stride + slot] = a; stk_j[level * stride + slot] = b; pending |= 1u << level; }
+                i -= a; j -= b; prefix <<= 1; e = c0; ++level;
+                continue;
+            }
+            if (has1) { i = a; j = b; prefix = (prefix << 1) | 1u; e = c1; ++level; continue; }
+        }
+        if (!pending) break;
+        const uint32_t l = 31u - static_cast<uint32_t>(__clz(pending));
+        pending &= ~(1u << l);
+        prefix = (prefix >> (level - (l + 1))) | 1u;           // ancestor at level l+1 is a left child: its right sibling
+        level = l + 1;
+        i = stk_i[l * stride + slot]; j = stk_j[l * stride + slot];
+        e = NodeEntry{0, 0};
+        if (level < L) e = load_node(v, (1u << level) + prefix);
+    }
+}
+
 // One warp expands one SA range.  Phase 1: level-synchronous frontier expansion, one lane per
 // frontier node, children compacted in order with a shuffle scan (frontier lives in shared memory).
 // Phase 2: once the frontier is wider than a warp, every lane walks its own subtrees depth-first.
+constexpr int kMaxLevels = 24;                 // wavelet-tree height bound (SEAL: 16)
 struct WarpFrontier {
     uint64_t i[2][64];
     uint64_t j[2][64];
     uint32_t prefix[2][64];
 };
+// shared memory one warp needs for warp_expand on a tree of height L: the frontier + 2 x L x 32 u64 of DFS stack
+__host__ __device__ inline size_t warp_expand_smem(uint32_t L) { return sizeof(WarpFrontier) + 2ull * L * 32 * 8; }
 
+// stk: 2 x L x 32 u64 of shared memory owned by this warp (pending right siblings of the depth-first phase)
 template <typename Sink>
-__device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, WarpFrontier& F) {
+__device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, WarpFrontier& F, uint64_t* stk) {
     if (lo >= hi) return;                                  // fm_index.cpp:98 `if (low == high) return`
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t L = v.L;
@@ -74,7 +131,7 @@ __device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sin
         cur = nxt; n = total; ++level;
     }
     for (uint32_t e = lane; e < n; e += 32)
-        expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+        expand_dfs_smem(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink, stk, stk + (size_t)L * 32, 32, (int)lane);
 }
 
 
@@ -93,11 +150,12 @@ struct BlockFrontierT {
     int count[2];
     int next;                       // work-queue cursor of the depth-first phase
 };
-using BlockFrontier = BlockFrontierT<1024>;   // 40 KB: five 256-thread CTAs per SM
+using BlockFrontier = BlockFrontierT<1024>;   // 40 KB (+ 80 KB of depth-first stack for 256 threads): two CTAs per SM
 constexpr uint64_t kWideRange = 2048;       // ranges at least this wide go to the block path
 
+// stk_i / stk_j: kMaxLevels x blockDim.x u64 each (shared memory) for the depth-first phase.
 template <typename Sink, typename Frontier>
-__device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, Frontier& F) {
+__device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, Frontier& F, uint64_t* stk_i, uint64_t* stk_j) {
     if (lo >= hi) return;                                      // uniform
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint32_t L = v.L;
@@ -138,7 +196,7 @@ __device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& si
     for (;;) {
         const int e = atomicAdd(&F.next, 1);
         if (e >= n) break;
-        expand_dfs(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink);
+        expand_dfs_smem(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink, stk_i, stk_j, nt, tid);
     }
     __syncthreads();
 }

@@ -70,46 +70,61 @@ __global__ void __launch_bounds__(128) lf_fold_kernel(FmView v, uint64_t nq, con
 }
 
 constexpr int kExpandWarps = 4;
+constexpr int kWideThreads = 256;
+
+// dynamic shared memory of the two kernel shapes for a tree of height L
+size_t narrow_smem(uint32_t L) { return kExpandWarps * warp_expand_smem(L); }
+size_t wide_smem(uint32_t L) { return sizeof(BlockFrontier) + 2ull * L * kWideThreads * 8; }
+
+__device__ __forceinline__ WarpFrontier& warp_frontier(unsigned char* smem, uint32_t L, uint32_t warp, uint64_t*& stk) {
+    unsigned char* base = smem + warp * warp_expand_smem(L);
+    stk = reinterpret_cast<uint64_t*>(base + sizeof(WarpFrontier));
+    return *reinterpret_cast<WarpFrontier*>(base);
+}
 
 // Allowed-token bitmask rows for R ranges (seal/beam_search.py:107,131-135).  mask is zeroed here.
-// wide_list[0] = number of wide rows found, wide_list[1..] = their indices (nullptr: expand everything here)
+// wide_list[0] = number of wide rows found, [1] = work cursor of the wide kernel, [2..] = their indices
+// (nullptr: expand everything here)
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_mask_kernel(
     FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
     uint32_t* __restrict__ mask, uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list) {
-    __shared__ WarpFrontier F[kExpandWarps];
+    extern __shared__ __align__(16) unsigned char expand_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* stk;
+    WarpFrontier& F = warp_frontier(expand_smem, v.L, warp, stk);
     for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
         uint32_t* row = mask + r * ld_words;
         for (uint32_t w = lane; w < ld_words; w += 32) row[w] = 0;
         __syncwarp();
         const uint64_t l = lo[r], h = hi[r];
         if (wide_list && h > l && h - l >= kWideRange) {       // defer to the block-cooperative kernel
-            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[1 + k] = r; }
+            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[2 + k] = r; }
             continue;
         }
         MaskSink sink{row, vocab, shift};
-        warp_expand(v, l, h, sink, F[warp]);
+        warp_expand(v, l, h, sink, F, stk);
         __syncwarp();
     }
 }
 
 // Persistent CTAs pull the wide rows found by expand_mask_kernel (device-side list, no host sync).
-__global__ void __launch_bounds__(256) expand_mask_wide_kernel(
+__global__ void __launch_bounds__(kWideThreads) expand_mask_wide_kernel(
     FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint32_t* __restrict__ mask,
-    uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list, unsigned long long* cursor) {
-    extern __shared__ __align__(16) unsigned char wide_smem[];
-    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem);
+    uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list) {
+    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem_raw);
+    uint64_t* stk = reinterpret_cast<uint64_t*>(wide_smem_raw + sizeof(BlockFrontier));
     __shared__ unsigned long long pick;
     const unsigned long long n = wide_list[0];
     for (;;) {
-        if (threadIdx.x == 0) pick = atomicAdd(cursor, 1ULL);
+        if (threadIdx.x == 0) pick = atomicAdd(wide_list + 1, 1ULL);
         __syncthreads();
         const unsigned long long k = pick;
         __syncthreads();
         if (k >= n) break;
-        const uint64_t r = wide_list[1 + k];
+        const uint64_t r = wide_list[2 + k];
         MaskSink sink{mask + r * ld_words, vocab, shift};
-        block_expand(v, lo[r], hi[r], sink, F);
+        block_expand(v, lo[r], hi[r], sink, F, stk, stk + (size_t)v.L * kWideThreads);
     }
 }
 
@@ -117,38 +132,41 @@ __global__ void __launch_bounds__(256) expand_mask_wide_kernel(
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_dense_kernel(
     FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
     uint64_t* __restrict__ dense, unsigned long long* wide_list) {
-    __shared__ WarpFrontier F[kExpandWarps];
+    extern __shared__ __align__(16) unsigned char expand_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t* stk;
+    WarpFrontier& F = warp_frontier(expand_smem, v.L, warp, stk);
     const uint64_t stride = 1ULL << v.L;
     for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
         const uint64_t l = lo[r], h = hi[r];
         if (wide_list && h > l && h - l >= kWideRange) {
-            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[1 + k] = r; }
+            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[2 + k] = r; }
             continue;
         }
         DenseSink sink{dense + r * stride};
-        warp_expand(v, l, h, sink, F[warp]);
+        warp_expand(v, l, h, sink, F, stk);
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(256) expand_dense_wide_kernel(
+__global__ void __launch_bounds__(kWideThreads) expand_dense_wide_kernel(
     FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t* __restrict__ dense,
-    unsigned long long* wide_list, unsigned long long* cursor) {
-    extern __shared__ __align__(16) unsigned char wide_smem[];
-    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem);
+    unsigned long long* wide_list) {
+    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
+    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem_raw);
+    uint64_t* stk = reinterpret_cast<uint64_t*>(wide_smem_raw + sizeof(BlockFrontier));
     __shared__ unsigned long long pick;
     const unsigned long long n = wide_list[0];
     const uint64_t stride = 1ULL << v.L;
     for (;;) {
-        if (threadIdx.x == 0) pick = atomicAdd(cursor, 1ULL);
+        if (threadIdx.x == 0) pick = atomicAdd(wide_list + 1, 1ULL);
         __syncthreads();
         const unsigned long long k = pick;
         __syncthreads();
         if (k >= n) break;
-        const uint64_t r = wide_list[1 + k];
+        const uint64_t r = wide_list[2 + k];
         DenseSink sink{dense + r * stride};
-        block_expand(v, lo[r], hi[r], sink, F);
+        block_expand(v, lo[r], hi[r], sink, F, stk, stk + (size_t)v.L * kWideThreads);
     }
 }
 
@@ -284,6 +302,24 @@ void release_device(sealfm_t* h) {
 }  // namespace
 
 namespace sealb200 {
+// Bitmask rows of R SA ranges: narrow ranges by one warp each, wide ones (>= kWideRange rows) by whole CTAs pulling
+// from a device-side work list.  `wide`: R + 2 u64 of scratch.  Stream-ordered, no host synchronisation; also the
+// tail of every decode step (decode.cu).
+void launch_expand_masks(const FmView& v, cudaStream_t s, uint64_t R, const uint64_t* lo_d, const uint64_t* hi_d, uint32_t* mask_d,
+                         uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide) {
+    if (v.L > kMaxLevels) throw ApiError(SEALFM_EINVAL, "wavelet tree higher than kMaxLevels");
+    CUDA_CHECK(cudaMemsetAsync(wide, 0, 2 * sizeof(unsigned long long), s));
+    const int ns = (int)narrow_smem(v.L), ws = (int)wide_smem(v.L);
+    static int ns_set = 0, ws_set = 0;
+    if (ns > ns_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ns)); ns_set = ns; }
+    if (ws > ws_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_mask_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws)); ws_set = ws; }
+    expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, ns, s>>>(v, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
+    CUDA_CHECK(cudaGetLastError());
+    const int wide_ctas = (int)std::min<uint64_t>(R, (uint64_t)sm_count() * 2);
+    expand_mask_wide_kernel<<<wide_ctas, kWideThreads, ws, s>>>(v, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
+    CUDA_CHECK(cudaGetLastError());
+}
+
 FmView sealfm_view(const sealfm_t* h) {
     if (!h) throw ApiError(SEALFM_EINVAL, "null handle");
     if (h->device < 0) throw ApiError(SEALFM_ENODEVICE, "index not bound to a CUDA device (call sealfm_to_device)");
@@ -420,18 +456,10 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, 
         if (!R) return;
         if ((uint64_t)ld_words * 32 < vocab) throw ApiError(SEALFM_EINVAL, "ld_words too small for vocab");
         cudaStream_t s = (cudaStream_t)stream;
-        unsigned long long* wide = nullptr;                    // [count, rows..., cursor]
+        unsigned long long* wide = nullptr;                    // [count, cursor, rows...]
         CUDA_CHECK(cudaMallocAsync(&wide, (R + 2) * sizeof(unsigned long long), s));
-        CUDA_CHECK(cudaMemsetAsync(wide, 0, sizeof(unsigned long long), s));
-        CUDA_CHECK(cudaMemsetAsync(wide + R + 1, 0, sizeof(unsigned long long), s));
-        expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, 0, s>>>(
-            h->view, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaFuncSetAttribute(expand_mask_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
-        expand_mask_wide_kernel<<<sm_count() * 5, 256, sizeof(BlockFrontier), s>>>(h->view, lo_d, hi_d, mask_d, ld_words, vocab, shift,
-                                                                                 wide, wide + R + 1);
-        CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaFreeAsync(wide, s));
+        struct Free { unsigned long long* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{wide, s};
+        launch_expand_masks(h->view, s, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
     });
 }
 
@@ -497,10 +525,12 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             CUDA_CHECK(cudaMemset(ddense.p, 0, cn * nsym * 8));
             DevBuf<unsigned long long> dwide(cn + 2);
             CUDA_CHECK(cudaMemset(dwide.p, 0, (cn + 2) * sizeof(unsigned long long)));
-            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32>>>(h->view, cn, dlo.p, dhi.p, ddense.p, dwide.p);
+            const int ns = (int)narrow_smem(L), ws = (int)wide_smem(L);
+            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ns));
+            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32, ns>>>(h->view, cn, dlo.p, dhi.p, ddense.p, dwide.p);
             CUDA_CHECK(cudaGetLastError());
-            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BlockFrontier)));
-            expand_dense_wide_kernel<<<sm_count() * 5, 256, sizeof(BlockFrontier)>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p, dwide.p + cn + 1);
+            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws));
+            expand_dense_wide_kernel<<<sm_count() * 2, kWideThreads, ws>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p);
             CUDA_CHECK(cudaGetLastError());
             compact_pairs_kernel<<<(unsigned)cn, 256>>>(L, ddense.p, doff.p, dout.p, dlen.p);
             CUDA_CHECK(cudaGetLastError());

@@ -416,3 +416,29 @@ def test_fm_index_generate_beyond_32_positions(kw):
     got = fm_index_generate(model, idx, ids, am, keep_history=True, **kw)
     worst = compare_generate(got, exp, ora, tol=2e-4)
     print(f"{kw}: worst |dscore| = {worst:.3e}")
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_beams=4, min_length=0, max_length=8, length_penalty=1.0, always_allow_eos=True),
+    dict(num_beams=3, min_length=2, max_length=7, length_penalty=0.0, always_allow_eos=True),
+    dict(num_beams=5, min_length=0, max_length=9, length_penalty=1.0, disable_fm_index=True),
+])
+def test_fm_index_generate_keep_history_false(kw):
+    """The signature's default scorer path (seal/beam_search.py:406,505-515; README.md:209-216): transformers' stock
+    BeamSearchScorer.  Oracle = the loop with the restated 4.13 scorer inside (parity unpinned for that class, see
+    oracle/decode_oracle.py); product = same kernels + host replay of the scorer over the records."""
+    import torch
+    from oracle.decode_oracle import fm_index_generate_oracle
+    from seal_b200.beam_search import fm_index_generate
+    docs, ora, idx, model = tiny_setup()
+    rng = np.random.default_rng(14)
+    ids, am = make_inputs(rng, Q=5, S=12, vocab=2000)
+    exp = fm_index_generate_oracle(model, ora, ids, am, keep_history=False, **kw)
+    got = fm_index_generate(model, idx, ids, am, **kw)                     # keep_history defaults to False
+    assert all(len(g) <= kw["num_beams"] for g in got)
+    worst = compare_generate(got, exp, ora)
+    print(f"keep_history=False {kw}: worst |dscore| = {worst:.3e}; hyps/query = {[len(x) for x in got]}")
+    if kw.get("disable_fm_index"):
+        seq_exp = fm_index_generate_oracle(model, ora, ids, am, keep_history=False, transformers_output=True, **kw)
+        seq_got = fm_index_generate(model, idx, ids, am, transformers_output=True, **kw)
+        assert torch.equal(seq_got.cpu(), seq_exp)

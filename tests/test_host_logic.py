@@ -231,3 +231,51 @@ def test_sdsl_format_writer_round_trip_and_reference_bytes(tmp_path):
         nat = str(tmp_path / "ours.native")
         fm.save(nat, native=True)
         assert np.array_equal(load_FMIndex(nat).section(0), fm.section(0))
+
+
+@pytest.mark.parametrize("lp,seed", [(0.0, 1), (1.0, 2), (0.7, 3), (1.0, 4)])
+def test_stock_scorer_replay_equals_scorer_in_the_loop(lp, seed):
+    """keep_history=False (seal/beam_search.py:505-515): the product replays transformers' stock BeamSearchScorer over
+    the per-step candidate records of the keep_history=True kernels.  Here, on the CPU, with a synthetic logit model
+    that ends hypotheses often: records rebuilt from the oracle's keep_history=True trace -> product replay, against
+    the oracle running the stock scorer INSIDE the loop (done queries padded, early exit, finalize)."""
+    import torch
+    from oracle.decode_oracle import constrained_beam_search_oracle
+    from seal_b200.beam_search import _replay_beam_search_scorer
+    V, B, T, Q, EOS, PAD = 40, 3, 9, 4, 2, 1
+    g = torch.Generator().manual_seed(seed)
+    table = torch.randn(V, V, generator=g) * 2.0
+    table[:, EOS] += 2.5                                         # hypotheses finish early and often
+
+    def step_logits(dec):
+        return table[dec[:, -1]] + 0.3 * table[dec[:, 0] * 0 + dec.shape[1] % V]
+
+    kw = dict(batch_size=Q, index=None, num_beams=B, min_length=0, max_length=T, length_penalty=lp, eos_token_id=EOS,
+              pad_token_id=PAD, decoder_start_token_id=EOS, model_eos_token_id=EOS, forced_eos_token_id=None,
+              disable_fm_index=True)
+    trace = []
+    constrained_beam_search_oracle(step_logits, trace=trace, **kw)
+    steps = [t for t in trace if "top_scores" in t]; fin = trace[-1]
+    H = len(steps) * 2 * B + B
+    rec = {"scores": np.zeros((Q, H), np.float32), "lens": np.zeros((Q, H), np.int32), "tokens": np.full((Q, H, T), PAD, np.int32)}
+    for st, t in enumerate(steps):
+        for q in range(Q):
+            for k in range(2 * B):
+                h = st * 2 * B + k
+                par = t["input_ids"][q * B + int(t["top_beams"][q, k])].tolist()
+                rec["scores"][q, h] = float(t["top_scores"][q, k]); rec["lens"][q, h] = len(par) + 1
+                rec["tokens"][q, h, :len(par) + 1] = par + [int(t["top_tokens"][q, k])]
+    for q in range(Q):
+        for j in range(B):
+            h = len(steps) * 2 * B + j
+            row = fin["final_input_ids"][q * B + j].tolist()
+            rec["scores"][q, h] = float(fin["final_beam_scores"][q * B + j]); rec["lens"][q, h] = len(row); rec["tokens"][q, h, :len(row)] = row
+    beams, seq, seq_scores = _replay_beam_search_scorer(rec, B, lp, EOS, PAD, T)
+    exp = constrained_beam_search_oracle(step_logits, keep_history=False, **kw)
+    exp_seq = constrained_beam_search_oracle(step_logits, keep_history=False, transformers_output=True, **kw)
+    got = [[(sc * (len(t) ** lp), t) for sc, t in b if sc > float("-inf")] for b in beams]
+    assert any(len(t) < T for b in got for _, t in b), "the case must contain finished hypotheses"
+    for qa, qb in zip(got, exp):
+        assert [t for _, t in qa] == [t for _, t, _ in qb]
+        assert all(abs(x[0] - y[0]) < 1e-5 for x, y in zip(qa, qb))
+    assert np.array_equal(seq, exp_seq.numpy())
