@@ -16,6 +16,11 @@ extern "C" {
 #endif
 
 const char* sealev_last_error(void);
+/* multi_key_score is Python's built-in sum() over the picked keys' scores (seal/keys.py:476): Neumaier-compensated since
+ * CPython 3.12, a plain left-to-right sum before (the reference pins Python 3.8/3.9).  compensated != 0 selects the
+ * former (default); seal_b200.keys sets it from the running interpreter so "the reference's result" follows the
+ * interpreter the reference would run under. */
+void sealev_set_sum_mode(int compensated);
 
 /* First stage (seal/keys.py:316-368): walks the located occurrences of the rare keys in key order --
  * occurrence j of key k (span_off[k] <= j < span_off[k+1]) ends at token position pos[j] in document doc[j] --

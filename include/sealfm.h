@@ -50,6 +50,13 @@ int sealfm_build(const uint64_t* symbols, uint64_t n, sealfm_t** out);
  * qsufsort + wt_int construction, sdsl/construct.hpp:120-166, sdsl/wt_int.hpp:169-256).  n + 1 < 2^31;
  * larger texts: sealfm_build.  SEALFM_ENODEVICE without a GPU. */
 int sealfm_build_gpu(const uint64_t* symbols, uint64_t n, int device, sealfm_t** out);
+/* Adopts index sections computed elsewhere -- exactly what sealfm_section() hands out of a built index: the
+ * level-concatenated wavelet-tree bits of csa_wt_int<> (sdsl/wt_int.hpp:202-242; size * max_level bits in n_tree
+ * words), the ascending alphabet (sigma symbols incl. the sentinel 0), the cumulative counts C (sigma + 1), SA[32 i]
+ * (ceil(size/32) entries) and ISA[64 i] ((size-1)/64 + 1 entries).  size = n + 1.  No consistency check beyond sizes. */
+int sealfm_from_sections(uint64_t size, uint32_t max_level, uint64_t sigma, const uint64_t* tree, uint64_t n_tree,
+                         const uint64_t* alphabet, const uint64_t* C, const uint64_t* sa_samples, uint64_t n_sa,
+                         const uint64_t* isa_samples, uint64_t n_isa, sealfm_t** out);
 /* FMIndex::initialize_from_file(file, width)         fm_index.cpp:43-48
  * file = raw little-endian integers of `width_bytes` (1,2,4,8) each; SEAL passes 4
  * (seal/index.py:18,62,65). */

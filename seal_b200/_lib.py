@@ -39,6 +39,7 @@ _FM_SIGS = {
     "sealfm_build": (i32, [vp, u64, C.POINTER(vp)]),
     "sealfm_build_gpu": (i32, [vp, u64, i32, C.POINTER(vp)]),
     "sealfm_save_sdsl": (i32, [vp, cp]),
+    "sealfm_from_sections": (i32, [u64, u32, u64, vp, u64, vp, vp, vp, u64, vp, u64, C.POINTER(vp)]),
     "sealfm_build_from_file": (i32, [cp, i32, C.POINTER(vp)]),
     "sealfm_load": (i32, [cp, C.POINTER(vp)]),
     "sealfm_save": (i32, [vp, cp]),
@@ -114,6 +115,7 @@ _DEC_SIGS = {
     "sealev_score_docs": (i32, [C.c_int64, vp, vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp, C.c_int64, i32, i32, i32, i32,
                                 C.c_double, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int64]),
     "sealev_last_error": (C.c_char_p, []),
+    "sealev_set_sum_mode": (None, [i32]),
     "sealdec_last_launch_count": (C.c_int64, [vp]),
     "sealdec_profile_gemm": (i32, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "sealdec_last_phase_us": (i32, [vp, C.POINTER(C.c_double)]),

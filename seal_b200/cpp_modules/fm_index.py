@@ -112,6 +112,10 @@ class FMIndex:
         check(lib.sealfm_build_from_file(os.fsencode(file), int(width), C.byref(out)))
         self._adopt(out.value)
 
+    def device_bytes(self):
+        """Bytes of the index resident on its GPU (0 before to_device)."""
+        return int(lib.sealfm_device_bytes(self._handle()))
+
     def size(self):                                               # fm_index.cpp:50-52
         return int(lib.sealfm_size(self._handle()))
 
@@ -138,11 +142,13 @@ class FMIndex:
             raise ValueError("lows and highs differ in length")
         offs = np.zeros(n + 1, dtype=np.uint64)
         h = self._dev()
-        check(lib.sealfm_distinct_count_multi(h, n, lo.ctypes.data, hi.ctypes.data, offs.ctypes.data, None, 0))
-        out = np.zeros(max(int(offs[n]), 1), dtype=np.uint64)
+        # a range holds at most min(width, 2^L) distinct symbols: size the output once instead of asking the library first
+        nsym = 1 << int(lib.sealfm_max_level(self._handle()))
+        cap = int(2 * np.minimum(np.where(hi > lo, hi - lo, 0), nsym).sum()) + 2
+        out = np.zeros(cap, dtype=np.uint64)
         check(lib.sealfm_distinct_count_multi(h, n, lo.ctypes.data, hi.ctypes.data, offs.ctypes.data,
                                               out.ctypes.data, len(out)))
-        flat = out.tolist()
+        flat = out[: int(offs[n])].tolist()
         o = offs.tolist()
         return [flat[o[i]:o[i + 1]] for i in range(n)]
 
@@ -226,6 +232,17 @@ class FMIndex:
                                        lo.contiguous().data_ptr(), hi_excl.contiguous().data_ptr(),
                                        out.data_ptr(), ld, vocab, shift))
         return out
+
+    @classmethod
+    def from_sections(cls, size, max_level, tree, alphabet, C_counts, sa_samples, isa_samples):
+        """Adopts sections computed elsewhere (sealfm_from_sections): what `section(0..4)` returns for a built index."""
+        t = _u64(tree); a = _u64(alphabet); c = _u64(C_counts); sa = _u64(sa_samples); isa = _u64(isa_samples)
+        out = vp()
+        check(lib.sealfm_from_sections(int(size), int(max_level), len(a), t.ctypes.data, len(t), a.ctypes.data, c.ctypes.data,
+                                       sa.ctypes.data, len(sa), isa.ctypes.data, len(isa), C.byref(out)))
+        obj = cls()
+        obj._adopt(out.value)
+        return obj
 
     def section(self, which):
         p = C.POINTER(u64)(); n = u64()

@@ -1249,13 +1249,12 @@ int sealdec_teacher_forced(sealbart_t* m, const int64_t* ids, const int64_t* mas
             int32_t* tk = m->st_tokens.as<int32_t>(); int32_t* an = m->st_anc.as<int32_t>();
             ids_to_tokens_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(rows, (int)T, (int)T, d_dec.as<int64_t>(), tk, an);
             CUDA_CHECK(cudaGetLastError());
-            const float inv_t = 1.0f / temperature;
             for (int p = 0; p < T; ++p) {
                 const bool need = (p + 1 < T) || (out_full && p == out_full_pos);
                 if (!need) continue;                           // the last position only feeds the full-vector output
                 decoder_step(cx, C, tk, p + 1, an, true, nullptr);
                 target_logprob_kernel<<<(unsigned)rows, 256, 0, s>>>(
-                    rows, C.V, C.ld, m->logits.as<float>(), d_dec.as<int64_t>() + (p + 1 < T ? p + 1 : 0), T, inv_t,
+                    rows, C.V, C.ld, m->logits.as<float>(), d_dec.as<int64_t>() + (p + 1 < T ? p + 1 : 0), T, temperature,
                     (p + 1 < T) ? d_out.as<float>() + p : nullptr, T - 1,
                     (out_full && p == out_full_pos) ? d_full.as<float>() : nullptr, C.V);
                 CUDA_CHECK(cudaGetLastError()); m->launches++;

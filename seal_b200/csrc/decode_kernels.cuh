@@ -551,14 +551,14 @@ __global__ void __launch_bounds__(256) apply_mask_kernel(int64_t R, int V, int64
 // optionally the whole log-prob row.  One CTA per row, single streaming pass for the statistics.
 __global__ void __launch_bounds__(256) target_logprob_kernel(int64_t R, int V, int64_t ld, const float* __restrict__ logits,
                                                              const int64_t* __restrict__ targets, int64_t tgt_stride,
-                                                             float inv_temperature, float* __restrict__ out,
+                                                             float temperature, float* __restrict__ out,
                                                              int64_t out_stride, float* __restrict__ full, int64_t full_ld) {
     __shared__ float red[8];
     const int64_t r = blockIdx.x;
     const float* lp = logits + r * ld;
     float mx = -INFINITY, se = 0.f;
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
-        const float x = lp[v] * inv_temperature;
+        const float x = lp[v] / temperature;              // the reference divides the logits (seal/keys.py:167)
         if (x > mx) { se *= expf(mx - x); mx = x; }
         if (mx > -INFINITY) se += expf(x - mx);
     }
@@ -568,9 +568,9 @@ __global__ void __launch_bounds__(256) target_logprob_kernel(int64_t R, int V, i
     const float logsum = logf(tot);
     if (out && threadIdx.x == 0) {
         const int64_t t = targets[r * tgt_stride];
-        out[r * out_stride] = (t >= 0 && t < V) ? (lp[t] * inv_temperature - bm) - logsum : 0.f;
+        out[r * out_stride] = (t >= 0 && t < V) ? (lp[t] / temperature - bm) - logsum : 0.f;
     }
     if (full)
-        for (int v = threadIdx.x; v < V; v += blockDim.x) full[r * full_ld + v] = (lp[v] * inv_temperature - bm) - logsum;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) full[r * full_ld + v] = (lp[v] / temperature - bm) - logsum;
 }
 }  // namespace sealb200

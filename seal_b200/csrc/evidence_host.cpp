@@ -45,12 +45,14 @@ struct Coverage {
 };
 
 thread_local std::string g_err;
+bool g_compensated_sum = true;      // how the host interpreter's built-in sum() adds floats (sealev_set_sum_mode)
 
 }  // namespace
 
 extern "C" {
 
 const char* sealev_last_error(void) { return g_err.c_str(); }
+void sealev_set_sum_mode(int compensated) { g_compensated_sum = compensated != 0; }
 
 int sealev_first_stage(int64_t n_keys, const int64_t* key_tok, const int64_t* key_off, const double* key_score,
                        const int64_t* key_count, int64_t empty_count, const int64_t* span_off,
@@ -201,7 +203,9 @@ int sealev_score_docs(int64_t n_keys, const int64_t* key_tok, const int64_t* key
             // (Python/bltinmodule.c); the fixtures were produced by the reference under 3.12, so this is what "the
             // reference's result" is here (a naive left-to-right sum differs in the last bit on 1 document of 200)
             double total = 0.0;
-            if (n_pick > first_pick) {
+            if (!g_compensated_sum) {                           // CPython < 3.12: plain left-to-right sum()
+                for (int64_t i = first_pick; i < n_pick; ++i) total += pick_score[i];
+            } else if (n_pick > first_pick) {
                 total = pick_score[first_pick];
                 double comp = 0.0;
                 for (int64_t i = first_pick + 1; i < n_pick; ++i) {

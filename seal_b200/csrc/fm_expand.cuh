@@ -16,9 +16,18 @@ struct MaskSink {
         if (tok < vocab) atomicOr(row + (tok >> 5), 1u << (tok & 31));
     }
 };
-struct DenseSink {
-    uint64_t* counts;     // 2^L entries for this range, zeroed
-    __device__ void operator()(uint32_t symbol, uint64_t ri, uint64_t rj) const { counts[symbol] = rj - ri; }
+// (symbol, count) pairs appended in discovery order to a per-range list + a presence bitmap over the symbol space;
+// order_pairs_kernel (fm_kernels.cu) turns that into the ascending-symbol output of FMIndex::distinct_count
+// (fm_index.cpp:91-109) without the reference's (and round 1's) dense sigma-wide scratch per range.
+struct PairSink {
+    uint64_t* list;           // this range's unordered pairs
+    unsigned int* counter;    // pairs appended so far
+    uint32_t* present;        // 2^L / 32 words, zeroed
+    __device__ void operator()(uint32_t symbol, uint64_t ri, uint64_t rj) const {
+        const unsigned int k = atomicAdd(counter, 1u);
+        list[2ull * k] = symbol; list[2ull * k + 1] = rj - ri;
+        atomicOr(present + (symbol >> 5), 1u << (symbol & 31));
+    }
 };
 
 // Depth-first expansion below (level, prefix) WITHOUT a local-memory stack.  A thread only ever has to remember
@@ -140,7 +149,7 @@ __device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sin
 // leaves one warp walking tens of thousands of tree nodes (measured tail: 3.5 ms for one row).  Here a
 // whole CTA expands one range: level-synchronous frontier in shared memory with atomic (unordered)
 // child append until there are at least two sub-trees per thread (or the buffer is full), then every
-// thread walks its sub-trees depth-first.  Sinks must be order-independent (bitmask OR / dense counts).
+// thread walks its sub-trees depth-first.  Sinks must be order-independent (bitmask OR / appended pairs).
 template <int CAP>
 struct BlockFrontierT {
     static constexpr int kCap = CAP;

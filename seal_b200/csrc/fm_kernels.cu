@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -34,6 +35,14 @@ struct sealfm {
     uint64_t* d_beginnings = nullptr;
     uint64_t device_bytes = 0;
     std::vector<uint64_t> beginnings;
+    // Host-pointer entry points: per-handle staging instead of a cudaMalloc / cudaFree pair per call.  Small calls
+    // (seal/retrieval.py:91 issues one get_count per key: 285 k per 1 000 queries) go through MAPPED pinned memory --
+    // the kernel reads its arguments from and writes its results to host memory directly: one launch + one stream
+    // synchronisation, no copies.  Larger calls use a grow-only device buffer.  Guarded by a mutex: re-entrant.
+    mutable std::mutex stage_mu;
+    mutable cudaStream_t stage_stream = nullptr;
+    mutable void* pin_h = nullptr; mutable void* pin_d = nullptr; mutable size_t pin_bytes = 0;
+    mutable void* dev_p = nullptr; mutable size_t dev_bytes = 0;
 };
 
 namespace {
@@ -42,17 +51,48 @@ namespace {
 // kernels
 // ------------------------------------------------------------------------------------------------
 
-// Batched LF step (FMIndex::backward_search_step, fm_index.cpp:67-76): one thread per triple.
+// Two LF steps walked in lockstep: four dependent rank chains (i, j of both symbols) are in flight per level, and the
+// next level's node entries are fetched with them.  One triple per thread (two chains) left the kernel latency-bound
+// beyond L2 -- 0.43-0.47 of the HBM copy peak at 30 % issue activity (profiles/r01_ncu_lf_200m_raw.csv).
+__device__ __forceinline__ void lf_step_pair(const FmView& v, uint64_t c0, uint64_t l0, uint64_t r0, uint64_t c1, uint64_t l1, uint64_t r1,
+                                             uint64_t& ol0, uint64_t& or0, uint64_t& ol1, uint64_t& or1) {
+    const uint32_t L = v.L;
+    const bool p0 = sym_present(v, c0), p1 = sym_present(v, c1);
+    const bool w0 = p0 && l0 == 0 && r0 + 1 == v.m, w1 = p1 && l1 == 0 && r1 + 1 == v.m;      // whole-range shortcut (:181-183)
+    const bool walk0 = p0 && !w0, walk1 = p1 && !w1;
+    const uint32_t s0 = walk0 ? (uint32_t)c0 : 0u, s1 = walk1 ? (uint32_t)c1 : 0u;
+    uint64_t i0 = walk0 ? l0 : 0, j0 = walk0 ? r0 + 1 : 0, i1 = walk1 ? l1 : 0, j1 = walk1 ? r1 + 1 : 0;
+    NodeEntry e0 = load_node(v, 1), e1 = e0;
+    for (uint32_t k = 0; k < L && (i0 | j0 | i1 | j1); ++k) {
+        NodeEntry n0 = e0, n1 = e1;
+        if (k + 1 < L) { n0 = load_node(v, (2u << k) + (s0 >> (L - 1 - k))); n1 = load_node(v, (2u << k) + (s1 >> (L - 1 - k))); }
+        const uint64_t a0 = rank1(v, e0.base + i0) - e0.ones, b0 = rank1(v, e0.base + j0) - e0.ones;
+        const uint64_t a1 = rank1(v, e1.base + i1) - e1.ones, b1 = rank1(v, e1.base + j1) - e1.ones;
+        if ((s0 >> (L - 1 - k)) & 1) { i0 = a0; j0 = b0; } else { i0 -= a0; j0 -= b0; }
+        if ((s1 >> (L - 1 - k)) & 1) { i1 = a1; j1 = b1; } else { i1 -= a1; j1 -= b1; }
+        e0 = n0; e1 = n1;
+    }
+    if (!p0) { ol0 = 1; or0 = 0; } else if (w0) { ol0 = v.csym[c0]; or0 = v.csym[c0 + 1] - 1; } else { const uint64_t cb = v.csym[c0]; ol0 = cb + i0; or0 = cb + j0 - 1; }
+    if (!p1) { ol1 = 1; or1 = 0; } else if (w1) { ol1 = v.csym[c1]; or1 = v.csym[c1 + 1] - 1; } else { const uint64_t cb = v.csym[c1]; ol1 = cb + i1; or1 = cb + j1 - 1; }
+}
+
+// Batched LF step (FMIndex::backward_search_step, fm_index.cpp:67-76): two triples per thread.
 __global__ void __launch_bounds__(256) lf_step_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ sym,
                                                       const uint64_t* __restrict__ lo,
                                                       const uint64_t* __restrict__ hi,
                                                       uint64_t* __restrict__ out_lo,
                                                       uint64_t* __restrict__ out_hi) {
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t l, r;
-        lf_step(v, sym[t], lo[t], hi[t], l, r);
-        out_lo[t] = l;
-        out_hi[t] = r;
+    const uint64_t half = (n + 1) / 2;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < half; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t u = t + half;
+        uint64_t l0, r0, l1, r1;
+        if (u < n) {
+            lf_step_pair(v, sym[t], lo[t], hi[t], sym[u], lo[u], hi[u], l0, r0, l1, r1);
+            out_lo[u] = l1; out_hi[u] = r1;
+        } else {
+            lf_step(v, sym[t], lo[t], hi[t], l0, r0);
+        }
+        out_lo[t] = l0; out_hi[t] = r0;
     }
 }
 
@@ -82,35 +122,47 @@ __device__ __forceinline__ WarpFrontier& warp_frontier(unsigned char* smem, uint
     return *reinterpret_cast<WarpFrontier*>(base);
 }
 
-// Allowed-token bitmask rows for R ranges (seal/beam_search.py:107,131-135).  mask is zeroed here.
-// wide_list[0] = number of wide rows found, [1] = work cursor of the wide kernel, [2..] = their indices
-// (nullptr: expand everything here)
-__global__ void __launch_bounds__(kExpandWarps * 32) expand_mask_kernel(
-    FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
-    uint32_t* __restrict__ mask, uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list) {
+// What a batch of SA ranges is expanded INTO: bitmask rows (the decode's allowed-token masks) or (symbol, count) pair lists.
+struct MaskRows {
+    uint32_t* mask; uint32_t ld_words, vocab, shift;
+    __device__ void clear(uint64_t r, uint32_t lane) const { uint32_t* row = mask + r * ld_words; for (uint32_t w = lane; w < ld_words; w += 32) row[w] = 0; }
+    __device__ MaskSink sink(uint64_t r) const { return MaskSink{mask + r * ld_words, vocab, shift}; }
+};
+struct PairRows {
+    uint64_t* list; const uint64_t* list_off; unsigned int* counters; uint32_t* present; uint32_t present_words;
+    __device__ void clear(uint64_t, uint32_t) const {}                      // counters / bitmaps are zeroed by one memset
+    __device__ PairSink sink(uint64_t r) const { return PairSink{list + list_off[r], counters + r, present + r * (uint64_t)present_words}; }
+};
+
+// One warp per range; wide ranges are deferred to the block-cooperative kernel through a device-side list:
+// wide_list[0] = number of wide rows found, [1] = work cursor of the wide kernel, [2..] = their indices.
+template <typename Rows>
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_rows_kernel(FmView v, uint64_t R, const uint64_t* __restrict__ lo,
+                                                                      const uint64_t* __restrict__ hi, Rows rows,
+                                                                      unsigned long long* wide_list) {
     extern __shared__ __align__(16) unsigned char expand_smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t* stk;
     WarpFrontier& F = warp_frontier(expand_smem, v.L, warp, stk);
     for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
-        uint32_t* row = mask + r * ld_words;
-        for (uint32_t w = lane; w < ld_words; w += 32) row[w] = 0;
+        rows.clear(r, lane);
         __syncwarp();
         const uint64_t l = lo[r], h = hi[r];
-        if (wide_list && h > l && h - l >= kWideRange) {       // defer to the block-cooperative kernel
+        if (h > l && h - l >= kWideRange) {
             if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[2 + k] = r; }
             continue;
         }
-        MaskSink sink{row, vocab, shift};
+        auto sink = rows.sink(r);
         warp_expand(v, l, h, sink, F, stk);
         __syncwarp();
     }
 }
 
-// Persistent CTAs pull the wide rows found by expand_mask_kernel (device-side list, no host sync).
-__global__ void __launch_bounds__(kWideThreads) expand_mask_wide_kernel(
-    FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint32_t* __restrict__ mask,
-    uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide_list) {
+// Persistent CTAs pull the wide rows found by expand_rows_kernel (no host sync).
+template <typename Rows>
+__global__ void __launch_bounds__(kWideThreads) expand_rows_wide_kernel(FmView v, const uint64_t* __restrict__ lo,
+                                                                       const uint64_t* __restrict__ hi, Rows rows,
+                                                                       unsigned long long* wide_list) {
     extern __shared__ __align__(16) unsigned char wide_smem_raw[];
     BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem_raw);
     uint64_t* stk = reinterpret_cast<uint64_t*>(wide_smem_raw + sizeof(BlockFrontier));
@@ -123,85 +175,49 @@ __global__ void __launch_bounds__(kWideThreads) expand_mask_wide_kernel(
         __syncthreads();
         if (k >= n) break;
         const uint64_t r = wide_list[2 + k];
-        MaskSink sink{mask + r * ld_words, vocab, shift};
+        auto sink = rows.sink(r);
         block_expand(v, lo[r], hi[r], sink, F, stk, stk + (size_t)v.L * kWideThreads);
     }
 }
 
-// Dense per-range symbol counts (scratch for the ordered (symbol,count) API output).
-__global__ void __launch_bounds__(kExpandWarps * 32) expand_dense_kernel(
-    FmView v, uint64_t R, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi,
-    uint64_t* __restrict__ dense, unsigned long long* wide_list) {
-    extern __shared__ __align__(16) unsigned char expand_smem[];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t* stk;
-    WarpFrontier& F = warp_frontier(expand_smem, v.L, warp, stk);
-    const uint64_t stride = 1ULL << v.L;
-    for (uint64_t r = blockIdx.x * (uint64_t)kExpandWarps + warp; r < R; r += (uint64_t)gridDim.x * kExpandWarps) {
-        const uint64_t l = lo[r], h = hi[r];
-        if (wide_list && h > l && h - l >= kWideRange) {
-            if (lane == 0) { const unsigned long long k = atomicAdd(wide_list, 1ULL); wide_list[2 + k] = r; }
-            continue;
-        }
-        DenseSink sink{dense + r * stride};
-        warp_expand(v, l, h, sink, F, stk);
-        __syncwarp();
-    }
-}
-
-__global__ void __launch_bounds__(kWideThreads) expand_dense_wide_kernel(
-    FmView v, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ hi, uint64_t* __restrict__ dense,
-    unsigned long long* wide_list) {
-    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
-    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem_raw);
-    uint64_t* stk = reinterpret_cast<uint64_t*>(wide_smem_raw + sizeof(BlockFrontier));
-    __shared__ unsigned long long pick;
-    const unsigned long long n = wide_list[0];
-    const uint64_t stride = 1ULL << v.L;
-    for (;;) {
-        if (threadIdx.x == 0) pick = atomicAdd(wide_list + 1, 1ULL);
-        __syncthreads();
-        const unsigned long long k = pick;
-        __syncthreads();
-        if (k >= n) break;
-        const uint64_t r = wide_list[2 + k];
-        DenseSink sink{dense + r * stride};
-        block_expand(v, lo[r], hi[r], sink, F, stk, stk + (size_t)v.L * kWideThreads);
-    }
-}
-
-// Ordered compaction of one dense count row into interleaved (symbol,count) pairs — one block per
-// range; out_off[r] is where range r's pairs start (in u64 units), out_len[r] receives 2k.
-__global__ void __launch_bounds__(256) compact_pairs_kernel(uint32_t L, const uint64_t* __restrict__ dense,
-                                                            const uint64_t* __restrict__ out_off,
-                                                            uint64_t* __restrict__ out,
-                                                            uint64_t* __restrict__ out_len) {
+// Unordered (symbol, count) pairs + presence bitmap -> ascending-symbol pairs: the position of a symbol is the number
+// of present symbols below it.  One CTA per range: block scan of the bitmap's popcounts, then a scatter.
+__global__ void __launch_bounds__(256) order_pairs_kernel(uint32_t present_words, const uint32_t* __restrict__ present,
+                                                          const unsigned int* __restrict__ counters,
+                                                          const uint64_t* __restrict__ list, const uint64_t* __restrict__ list_off,
+                                                          uint64_t* __restrict__ out, uint64_t* __restrict__ out_len) {
+    extern __shared__ uint32_t pre[];                           // exclusive prefix of popcounts, present_words entries
     __shared__ uint32_t warp_tot[8];
     __shared__ uint32_t carry;
     const uint64_t r = blockIdx.x;
-    const uint64_t nsym = 1ULL << L;
-    const uint64_t* row = dense + r * nsym;
-    uint64_t* dst = out + out_off[r];
+    const uint32_t* bm = present + r * (uint64_t)present_words;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    for (uint64_t basei = 0; basei < nsym; basei += blockDim.x) {
-        const uint64_t s = basei + threadIdx.x;
-        const uint64_t c = s < nsym ? row[s] : 0;
-        const uint32_t flag = c != 0;
-        const uint32_t ball = __ballot_sync(0xffffffffu, flag);
-        const uint32_t pre = __popc(ball & ((1u << lane) - 1));
-        if (lane == 0) warp_tot[warp] = __popc(ball);
+    for (uint32_t w0 = 0; w0 < present_words; w0 += blockDim.x) {
+        const uint32_t w = w0 + threadIdx.x;
+        const uint32_t c = w < present_words ? __popc(bm[w]) : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += t; }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         uint32_t woff = 0, tot = 0;
-        for (uint32_t w = 0; w < blockDim.x / 32; ++w) { if (w < warp) woff += warp_tot[w]; tot += warp_tot[w]; }
-        const uint32_t pos = carry + woff + pre;
-        if (flag) { dst[2ULL * pos] = s; dst[2ULL * pos + 1] = c; }
+        for (uint32_t x = 0; x < blockDim.x / 32; ++x) { if (x < warp) woff += warp_tot[x]; tot += warp_tot[x]; }
+        if (w < present_words) pre[w] = carry + woff + incl - c;
         __syncthreads();
         if (threadIdx.x == 0) carry += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out_len[r] = 2ULL * carry;
+    const unsigned int k = counters[r];
+    const uint64_t* src = list + list_off[r];
+    uint64_t* dst = out + list_off[r];
+    for (unsigned int p = threadIdx.x; p < k; p += blockDim.x) {
+        const uint64_t sym = src[2ull * p], cnt = src[2ull * p + 1];
+        const uint32_t pos = pre[sym >> 5] + __popc(bm[sym >> 5] & ((1u << (sym & 31)) - 1u));
+        dst[2ull * pos] = sym; dst[2ull * pos + 1] = cnt;
+    }
+    if (threadIdx.x == 0) out_len[r] = 2ull * k;
 }
 
 __global__ void __launch_bounds__(128) locate_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ rows,
@@ -238,6 +254,76 @@ struct DevBuf {
     ~DevBuf() { if (p) cudaFree(p); }
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// Per-call view of the handle's staging area (see struct sealfm): a bump allocator over the mapped pinned buffer
+// (small calls: the kernels read / write host memory directly, no copies) or the grow-only device buffer.
+class Stage {
+public:
+    static constexpr size_t kMappedMax = 96 * 1024;
+    // device_only: the kernels use atomics on the staged memory (not guaranteed on mapped host memory)
+    Stage(const sealfm_t* h, size_t bytes_needed, bool device_only = false) : h_(h), lk_(h->stage_mu) {
+        bytes_needed += 256;
+        if (!h->stage_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&h->stage_stream, cudaStreamNonBlocking));
+        mapped_ = !device_only && bytes_needed <= kMappedMax;
+        if (mapped_) {
+            if (!h->pin_h) {
+                CUDA_CHECK(cudaHostAlloc(&h->pin_h, kMappedMax, cudaHostAllocMapped));
+                CUDA_CHECK(cudaHostGetDevicePointer(&h->pin_d, h->pin_h, 0));
+                h->pin_bytes = kMappedMax;
+            }
+            cap_ = h->pin_bytes;
+        } else {
+            if (h->dev_bytes < bytes_needed) {
+                if (h->dev_p) { CUDA_CHECK(cudaStreamSynchronize(h->stage_stream)); cudaFree(h->dev_p); h->dev_p = nullptr; h->dev_bytes = 0; }
+                const size_t want = std::max(bytes_needed, (size_t)1 << 20);
+                CUDA_CHECK(cudaMalloc(&h->dev_p, want));
+                h->dev_bytes = want;
+            }
+            cap_ = h->dev_bytes;
+        }
+    }
+    cudaStream_t stream() const { return h_->stage_stream; }
+    // device-usable region of `bytes` (16-byte aligned); *host_alias (mapped mode only) is the same memory seen from the host
+    void* reserve(size_t bytes, void** host_alias = nullptr) {
+        const size_t off = used_;
+        used_ = (used_ + bytes + 15) / 16 * 16;
+        if (used_ > cap_) throw ApiError(SEALFM_ENOMEM, "internal: staging area too small");
+        if (host_alias) *host_alias = mapped_ ? static_cast<char*>(h_->pin_h) + off : nullptr;
+        return static_cast<char*>(mapped_ ? h_->pin_d : h_->dev_p) + off;
+    }
+    // input: a device-usable copy of src[0..bytes)
+    void* put(const void* src, size_t bytes) {
+        void* alias = nullptr;
+        void* d = reserve(bytes, &alias);
+        if (!bytes) return d;
+        if (mapped_) std::memcpy(alias, src, bytes);
+        else CUDA_CHECK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, stream()));
+        return d;
+    }
+    void zero(void* d, size_t bytes) {
+        if (!bytes) return;
+        if (mapped_) std::memset(static_cast<char*>(h_->pin_h) + (static_cast<char*>(d) - static_cast<char*>(h_->pin_d)), 0, bytes);
+        else CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, stream()));
+    }
+    // output: after sync(), dst holds the `bytes` at device-usable pointer d
+    void get(void* dst, const void* d, size_t bytes) {
+        if (!bytes) return;
+        if (mapped_) pending_.push_back({dst, static_cast<const char*>(h_->pin_h) + (static_cast<const char*>(d) - static_cast<const char*>(h_->pin_d)), bytes});
+        else CUDA_CHECK(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, stream()));
+    }
+    void sync() {
+        CUDA_CHECK(cudaStreamSynchronize(stream()));
+        for (auto& p : pending_) std::memcpy(p.dst, p.src, p.bytes);
+        pending_.clear();
+    }
+private:
+    struct Pending { void* dst; const void* src; size_t bytes; };
+    const sealfm_t* h_;
+    std::unique_lock<std::mutex> lk_;
+    bool mapped_ = false;
+    size_t cap_ = 0, used_ = 0;
+    std::vector<Pending> pending_;
 };
 
 void require_device(const sealfm_t* h) {
@@ -296,6 +382,12 @@ void release_device(sealfm_t* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_blocks); cudaFree(h->d_csym); cudaFree(h->d_node_tab);
     cudaFree(h->d_sa); cudaFree(h->d_isa); cudaFree(h->d_beginnings);
+    h->d_blocks = nullptr; h->d_csym = nullptr; h->d_node_tab = nullptr;       // a later re-bind must not see (or free) these again
+    h->d_sa = nullptr; h->d_isa = nullptr; h->d_beginnings = nullptr;
+    h->view = FmView{};
+    if (h->stage_stream) { cudaStreamSynchronize(h->stage_stream); cudaStreamDestroy(h->stage_stream); h->stage_stream = nullptr; }
+    if (h->pin_h) { cudaFreeHost(h->pin_h); h->pin_h = nullptr; h->pin_d = nullptr; h->pin_bytes = 0; }
+    if (h->dev_p) { cudaFree(h->dev_p); h->dev_p = nullptr; h->dev_bytes = 0; }
     h->device = -1;
 }
 
@@ -311,12 +403,13 @@ void launch_expand_masks(const FmView& v, cudaStream_t s, uint64_t R, const uint
     CUDA_CHECK(cudaMemsetAsync(wide, 0, 2 * sizeof(unsigned long long), s));
     const int ns = (int)narrow_smem(v.L), ws = (int)wide_smem(v.L);
     static int ns_set = 0, ws_set = 0;
-    if (ns > ns_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ns)); ns_set = ns; }
-    if (ws > ws_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_mask_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws)); ws_set = ws; }
-    expand_mask_kernel<<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, ns, s>>>(v, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
+    if (ns > ns_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_rows_kernel<MaskRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ns)); ns_set = ns; }
+    if (ws > ws_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_rows_wide_kernel<MaskRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws)); ws_set = ws; }
+    const MaskRows rows{mask_d, ld_words, vocab, shift};
+    expand_rows_kernel<MaskRows><<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, ns, s>>>(v, R, lo_d, hi_d, rows, wide);
     CUDA_CHECK(cudaGetLastError());
     const int wide_ctas = (int)std::min<uint64_t>(R, (uint64_t)sm_count() * 2);
-    expand_mask_wide_kernel<<<wide_ctas, kWideThreads, ws, s>>>(v, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
+    expand_rows_wide_kernel<MaskRows><<<wide_ctas, kWideThreads, ws, s>>>(v, lo_d, hi_d, rows, wide);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -468,14 +561,15 @@ int sealfm_backward_search_step(const sealfm_t* h, uint64_t n, const uint64_t* s
     return guarded([&] {
         require_device(h);
         if (!n) return;
-        DevBuf<uint64_t> d(5 * n);
-        CUDA_CHECK(cudaMemcpy(d.p, sym, n * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d.p + n, lo, n * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(d.p + 2 * n, hi, n * 8, cudaMemcpyHostToDevice));
-        lf_step_kernel<<<grid_for(n, 256), 256>>>(h->view, n, d.p, d.p + n, d.p + 2 * n, d.p + 3 * n, d.p + 4 * n);
+        Stage st(h, 5 * n * 8 + 128);
+        const uint64_t* ds = (const uint64_t*)st.put(sym, n * 8);
+        const uint64_t* dl = (const uint64_t*)st.put(lo, n * 8);
+        const uint64_t* dh = (const uint64_t*)st.put(hi, n * 8);
+        uint64_t* ol = (uint64_t*)st.reserve(n * 8); uint64_t* oh = (uint64_t*)st.reserve(n * 8);
+        lf_step_kernel<<<grid_for((n + 1) / 2, 256), 256, 0, st.stream()>>>(h->view, n, ds, dl, dh, ol, oh);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemcpy(out_lo, d.p + 3 * n, n * 8, cudaMemcpyDeviceToHost));
-        CUDA_CHECK(cudaMemcpy(out_hi, d.p + 4 * n, n * 8, cudaMemcpyDeviceToHost));
+        st.get(out_lo, ol, n * 8); st.get(out_hi, oh, n * 8);
+        st.sync();
     });
 }
 
@@ -485,13 +579,14 @@ int sealfm_backward_search_multi(const sealfm_t* h, uint64_t nq, const uint64_t*
         require_device(h);
         if (!nq) return;
         const uint64_t tot = offsets[nq];
-        DevBuf<uint64_t> ds(tot), doff(nq + 1), dout(2 * nq);
-        if (tot) CUDA_CHECK(cudaMemcpy(ds.p, symbols, tot * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(doff.p, offsets, (nq + 1) * 8, cudaMemcpyHostToDevice));
-        lf_fold_kernel<<<grid_for(nq, 128), 128>>>(h->view, nq, ds.p, doff.p, dout.p, dout.p + nq);
+        Stage st(h, (tot + 3 * nq + 1) * 8 + 128);
+        const uint64_t* ds = (const uint64_t*)st.put(symbols, tot * 8);
+        const uint64_t* doff = (const uint64_t*)st.put(offsets, (nq + 1) * 8);
+        uint64_t* ol = (uint64_t*)st.reserve(nq * 8); uint64_t* oh = (uint64_t*)st.reserve(nq * 8);
+        lf_fold_kernel<<<grid_for(nq, 128), 128, 0, st.stream()>>>(h->view, nq, ds, doff, ol, oh);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemcpy(out_lo, dout.p, nq * 8, cudaMemcpyDeviceToHost));
-        CUDA_CHECK(cudaMemcpy(out_hi, dout.p + nq, nq * 8, cudaMemcpyDeviceToHost));
+        st.get(out_lo, ol, nq * 8); st.get(out_hi, oh, nq * 8);
+        st.sync();
     });
 }
 
@@ -501,53 +596,62 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
         require_device(h);
         if (!out_offsets || (!lows && n) || (!highs && n)) throw ApiError(SEALFM_EINVAL, "null argument");
         const uint32_t L = h->host.max_level;
+        if (L > kMaxLevels) throw ApiError(SEALFM_EINVAL, "wavelet tree higher than kMaxLevels");
         const uint64_t nsym = 1ULL << L;
-        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(64, (1ULL << 25) / (nsym * 8)));
-        std::vector<uint64_t> lens(n, 0);
-        std::vector<std::vector<uint64_t>> pieces;      // per chunk: packed results (upper-bound layout)
-        std::vector<std::vector<uint64_t>> piece_off;
-        pieces.reserve((n + chunk - 1) / chunk);
-        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
-            const uint64_t cn = std::min(chunk, n - c0);
-            std::vector<uint64_t> ub(cn + 1, 0);        // upper bound on 2k per range
-            for (uint64_t i = 0; i < cn; ++i) {
-                uint64_t lo = lows[c0 + i], hi = highs[c0 + i];
-                // hi == size()+1 is reachable through the reference's first-step quirk;
-                // the arithmetic below is the reference's own for such a range.
-                if (hi > h->host.size + 1) throw ApiError(SEALFM_EINVAL, "range end beyond size()+1");
-                uint64_t k = hi > lo ? std::min<uint64_t>(hi - lo, nsym) : 0;
-                ub[i + 1] = ub[i] + 2 * k;
-            }
-            DevBuf<uint64_t> dlo(cn), dhi(cn), ddense(cn * nsym), doff(cn + 1), dout(ub[cn]), dlen(cn);
-            CUDA_CHECK(cudaMemcpy(dlo.p, lows + c0, cn * 8, cudaMemcpyHostToDevice));
-            CUDA_CHECK(cudaMemcpy(dhi.p, highs + c0, cn * 8, cudaMemcpyHostToDevice));
-            CUDA_CHECK(cudaMemcpy(doff.p, ub.data(), (cn + 1) * 8, cudaMemcpyHostToDevice));
-            CUDA_CHECK(cudaMemset(ddense.p, 0, cn * nsym * 8));
-            DevBuf<unsigned long long> dwide(cn + 2);
-            CUDA_CHECK(cudaMemset(dwide.p, 0, (cn + 2) * sizeof(unsigned long long)));
-            const int ns = (int)narrow_smem(L), ws = (int)wide_smem(L);
-            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ns));
-            expand_dense_kernel<<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32, ns>>>(h->view, cn, dlo.p, dhi.p, ddense.p, dwide.p);
-            CUDA_CHECK(cudaGetLastError());
-            CUDA_CHECK(cudaFuncSetAttribute(expand_dense_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws));
-            expand_dense_wide_kernel<<<sm_count() * 2, kWideThreads, ws>>>(h->view, dlo.p, dhi.p, ddense.p, dwide.p);
-            CUDA_CHECK(cudaGetLastError());
-            compact_pairs_kernel<<<(unsigned)cn, 256>>>(L, ddense.p, doff.p, dout.p, dlen.p);
-            CUDA_CHECK(cudaGetLastError());
-            pieces.emplace_back(ub[cn]);
-            if (ub[cn]) CUDA_CHECK(cudaMemcpy(pieces.back().data(), dout.p, ub[cn] * 8, cudaMemcpyDeviceToHost));
-            CUDA_CHECK(cudaMemcpy(lens.data() + c0, dlen.p, cn * 8, cudaMemcpyDeviceToHost));
-            piece_off.push_back(std::move(ub));
+        const uint32_t words = (uint32_t)((nsym + 31) / 32);
+        // upper bound on the pairs of a range: its width, or the alphabet (hi == size()+1 is reachable through the
+        // reference's first-step quirk; the arithmetic below is the reference's own for such a range)
+        std::vector<uint64_t> ub(n + 1, 0);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (highs[i] > h->host.size + 1) throw ApiError(SEALFM_EINVAL, "range end beyond size()+1");
+            const uint64_t k = highs[i] > lows[i] ? std::min<uint64_t>(highs[i] - lows[i], nsym) : 0;
+            ub[i + 1] = ub[i] + 2 * k;
         }
+        std::vector<uint64_t> lens(n, 0), tmp;
         out_offsets[0] = 0;
-        for (uint64_t i = 0; i < n; ++i) out_offsets[i + 1] = out_offsets[i] + lens[i];
-        if (!out) return;
-        if (out_offsets[n] > out_cap) throw ApiError(SEALFM_ECAPACITY, "output buffer too small");
-        for (uint64_t c0 = 0, pc = 0; c0 < n; c0 += chunk, ++pc) {
-            const uint64_t cn = std::min(chunk, n - c0);
-            for (uint64_t i = 0; i < cn; ++i)
-                if (lens[c0 + i])
-                    std::memcpy(out + out_offsets[c0 + i], pieces[pc].data() + piece_off[pc][i], lens[c0 + i] * 8);
+        const uint64_t kChunkPairs = 1ULL << 24;                // u64 of list scratch per pass (2 x 128 MB at most)
+        const int ns = (int)narrow_smem(L), ws = (int)wide_smem(L);
+        CUDA_CHECK(cudaFuncSetAttribute(expand_rows_kernel<PairRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ns));
+        CUDA_CHECK(cudaFuncSetAttribute(expand_rows_wide_kernel<PairRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws));
+        uint64_t written = 0;
+        for (uint64_t c0 = 0; c0 < n;) {
+            uint64_t c1 = c0 + 1;
+            while (c1 < n && ub[c1 + 1] - ub[c0] <= kChunkPairs && c1 - c0 < 4096) ++c1;
+            const uint64_t cn = c1 - c0, pairs = ub[c1] - ub[c0];
+            std::vector<uint64_t> off(cn + 1);
+            for (uint64_t i = 0; i <= cn; ++i) off[i] = ub[c0 + i] - ub[c0];
+            const size_t zero_bytes = (cn * 4 + 15) / 16 * 16 + (size_t)cn * words * 4 + (cn + 2) * 8;
+            Stage st(h, (2 * cn + cn + 1 + 2 * pairs + cn) * 8 + zero_bytes + 256, true);
+            const uint64_t* dlo = (const uint64_t*)st.put(lows + c0, cn * 8);
+            const uint64_t* dhi = (const uint64_t*)st.put(highs + c0, cn * 8);
+            const uint64_t* doff = (const uint64_t*)st.put(off.data(), (cn + 1) * 8);
+            uint64_t* dlist = (uint64_t*)st.reserve(pairs * 8); uint64_t* dout = (uint64_t*)st.reserve(pairs * 8);
+            uint64_t* dlen = (uint64_t*)st.reserve(cn * 8);
+            char* z = (char*)st.reserve(zero_bytes);
+            st.zero(z, zero_bytes);
+            unsigned int* dcnt = (unsigned int*)z;
+            uint32_t* dpresent = (uint32_t*)(z + (cn * 4 + 15) / 16 * 16);
+            unsigned long long* dwide = (unsigned long long*)(z + (cn * 4 + 15) / 16 * 16 + (size_t)cn * words * 4);
+            const PairRows rows{dlist, doff, dcnt, dpresent, words};
+            expand_rows_kernel<PairRows><<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32, ns, st.stream()>>>(h->view, cn, dlo, dhi, rows, dwide);
+            CUDA_CHECK(cudaGetLastError());
+            expand_rows_wide_kernel<PairRows><<<(int)std::min<uint64_t>(cn, (uint64_t)sm_count() * 2), kWideThreads, ws, st.stream()>>>(h->view, dlo, dhi, rows, dwide);
+            CUDA_CHECK(cudaGetLastError());
+            order_pairs_kernel<<<(unsigned)cn, 256, words * 4, st.stream()>>>(words, dpresent, dcnt, dlist, doff, dout, dlen);
+            CUDA_CHECK(cudaGetLastError());
+            st.get(lens.data() + c0, dlen, cn * 8);
+            if (out) { tmp.resize(pairs); st.get(tmp.data(), dout, pairs * 8); }
+            st.sync();
+            for (uint64_t i = 0; i < cn; ++i) {
+                const uint64_t len = lens[c0 + i];
+                out_offsets[c0 + i + 1] = out_offsets[c0 + i] + len;
+                if (out && len) {
+                    if (written + len > out_cap) throw ApiError(SEALFM_ECAPACITY, "output buffer too small");
+                    std::memcpy(out + written, tmp.data() + off[i], len * 8);
+                }
+                written += len;
+            }
+            c0 = c1;
         }
     });
 }
@@ -557,11 +661,13 @@ static int locate_impl(const sealfm_t* h, uint64_t n, const uint64_t* rows, uint
         require_device(h);
         if (!n) return;
         if (want_doc && !h->view.beginnings) throw ApiError(SEALFM_EINVAL, "sealfm_set_beginnings not called");
-        DevBuf<uint64_t> d(2 * n);
-        CUDA_CHECK(cudaMemcpy(d.p, rows, n * 8, cudaMemcpyHostToDevice));
-        locate_kernel<<<grid_for(n, 128), 128>>>(h->view, n, d.p, d.p + n, want_doc);
+        Stage st(h, 2 * n * 8 + 128);
+        const uint64_t* dr = (const uint64_t*)st.put(rows, n * 8);
+        uint64_t* dout = (uint64_t*)st.reserve(n * 8);
+        locate_kernel<<<grid_for(n, 128), 128, 0, st.stream()>>>(h->view, n, dr, dout, want_doc);
         CUDA_CHECK(cudaGetLastError());
-        CUDA_CHECK(cudaMemcpy(out, d.p + n, n * 8, cudaMemcpyDeviceToHost));
+        st.get(out, dout, n * 8);
+        st.sync();
     });
 }
 int sealfm_locate(const sealfm_t* h, uint64_t n, const uint64_t* rows, uint64_t* out_pos) {
@@ -584,13 +690,37 @@ int sealfm_extract_text(const sealfm_t* h, uint64_t n, const uint64_t* begins, c
         if (!out || !n) return;
         const uint64_t tot = out_offsets[n];
         if (tot > out_cap) throw ApiError(SEALFM_ECAPACITY, "output buffer too small");
-        DevBuf<uint64_t> db(n), de(n), doff(n + 1), dout(tot);
-        CUDA_CHECK(cudaMemcpy(db.p, begins, n * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(de.p, ends, n * 8, cudaMemcpyHostToDevice));
-        CUDA_CHECK(cudaMemcpy(doff.p, out_offsets, (n + 1) * 8, cudaMemcpyHostToDevice));
-        extract_kernel<<<grid_for(n, 64), 64>>>(h->view, n, db.p, de.p, doff.p, dout.p);
+        Stage st(h, (3 * n + 1 + tot) * 8 + 128);
+        const uint64_t* db = (const uint64_t*)st.put(begins, n * 8);
+        const uint64_t* de = (const uint64_t*)st.put(ends, n * 8);
+        const uint64_t* doff = (const uint64_t*)st.put(out_offsets, (n + 1) * 8);
+        uint64_t* dout = (uint64_t*)st.reserve(tot * 8);
+        extract_kernel<<<grid_for(n, 64), 64, 0, st.stream()>>>(h->view, n, db, de, doff, dout);
         CUDA_CHECK(cudaGetLastError());
-        if (tot) CUDA_CHECK(cudaMemcpy(out, dout.p, tot * 8, cudaMemcpyDeviceToHost));
+        st.get(out, dout, tot * 8);
+        st.sync();
+    });
+}
+
+/* An index whose sections were computed elsewhere (same content sealfm_section hands out). */
+int sealfm_from_sections(uint64_t size, uint32_t max_level, uint64_t sigma, const uint64_t* tree, uint64_t n_tree,
+                         const uint64_t* alphabet, const uint64_t* C, const uint64_t* sa_samples, uint64_t n_sa,
+                         const uint64_t* isa_samples, uint64_t n_isa, sealfm_t** out) {
+    return guarded([&] {
+        if (!out || !tree || !alphabet || !C || !sa_samples || !isa_samples) throw ApiError(SEALFM_EINVAL, "null argument");
+        if (!size || !max_level || max_level > kMaxLevels || !sigma) throw ApiError(SEALFM_EINVAL, "bad size / max_level / sigma");
+        const uint64_t bits = size * (uint64_t)max_level;
+        if (n_tree != (bits + 63) / 64) throw ApiError(SEALFM_EINVAL, "tree must hold size * max_level bits");
+        if (n_sa != (size + 31) / 32 || n_isa != (size - 1) / 64 + 1) throw ApiError(SEALFM_EINVAL, "sample arrays have the wrong length");
+        std::unique_ptr<sealfm> h(new sealfm());
+        HostIndex& H = h->host;
+        H.size = size; H.max_level = max_level; H.sigma = sigma;
+        H.tree.assign(tree, tree + n_tree);
+        H.alphabet.assign(alphabet, alphabet + sigma);
+        H.C.assign(C, C + sigma + 1);
+        H.sa_samples.assign(sa_samples, sa_samples + n_sa);
+        H.isa_samples.assign(isa_samples, isa_samples + n_isa);
+        *out = h.release();
     });
 }
 

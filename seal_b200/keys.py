@@ -7,6 +7,8 @@ No CPU path."""
 import ctypes as C
 from typing import List, Optional
 
+import sys
+
 import numpy as np
 
 from ._lib import lib, check
@@ -69,9 +71,8 @@ def rescore_keys(model, inputs, list_of_decoded, batch_size=100, length_penalty=
     for r, toks in enumerate(rows):
         dec[r, :len(toks)] = toks
     lp, _ = _teacher_forced(eng, ids, mask, dec, row_query)
-    lp = lp.astype(np.float64)
     lp[dec[:, 1:] < 2] = 0.0                                                     # :132
-    lp = lp[:, len(prefix):].sum(-1)                                             # :133-134
+    lp = lp[:, len(prefix):].sum(-1, dtype=np.float32)                           # :133-134 (the reference sums the fp32 tensor)
     for q, di, ll in zip(row_query, orig, lp.tolist()):
         all_out[q].append((ll / (len(di) ** length_penalty), di))                # :138-139
     return [v for k, v in sorted(all_out.items())]
@@ -263,15 +264,24 @@ def aggregate_evidence(ngrams_and_scores, unigram_scores: Optional[List[float]] 
     n = len(docs_tok)
     out_score = np.zeros(max(n, 1)); out_best = np.zeros(max(n, 1), dtype=np.int64); out_best_score = np.zeros(max(n, 1))
     pick_off = np.zeros(n + 1, dtype=np.int64)
-    cap = int(doc_off[-1]) * 2 + 16                       # a document cannot pick more keys + unigram types than it has tokens
-    pick_key = np.zeros(cap, dtype=np.int64); pick_score = np.zeros(cap)
-    _evcheck(lib.sealev_score_docs(len(sk), sk.tok.ctypes.data, sk.off.ctypes.data, sk.score.ctypes.data, sk.count.ctypes.data,
+    # a document cannot pick more keys + unigram types than it has tokens -- when overlaps are forbidden.  With
+    # allow_overlaps every nested / overlapping match is picked, so the buffer simply grows on SEALFM_ECAPACITY.
+    cap = int(doc_off[-1]) * 2 + 16
+    lib.sealev_set_sum_mode(1 if sys.version_info >= (3, 12) else 0)     # how this interpreter's sum() adds floats (:476)
+    while True:
+        pick_key = np.zeros(cap, dtype=np.int64); pick_score = np.zeros(cap)
+        rc = lib.sealev_score_docs(len(sk), sk.tok.ctypes.data, sk.off.ctypes.data, sk.score.ctypes.data, sk.count.ctypes.data,
                                    empty_count, n, flat.ctypes.data, doc_off.ctypes.data,
                                    uni.ctypes.data if uni is not None else None, len(uni) if uni is not None else 0, sort_mode,
                                    int(bool(allow_overlaps)), int(bool(unigrams_ignore_free_places)),
                                    int(bool(single_key_add_unigrams)), float(beta), float(single_key), out_score.ctypes.data,
                                    out_best.ctypes.data, out_best_score.ctypes.data, pick_off.ctypes.data, pick_key.ctypes.data,
-                                   pick_score.ctypes.data, cap))
+                                   pick_score.ctypes.data, cap)
+        if rc == -6 and cap < (1 << 34):             # SEALFM_ECAPACITY
+            cap *= 4
+            continue
+        _evcheck(rc)
+        break
     results = {}
     pk, ps, po = pick_key.tolist(), pick_score.tolist(), pick_off.tolist()
     for i, d in enumerate(shortlist):

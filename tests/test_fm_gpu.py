@@ -232,3 +232,48 @@ def test_gpu_index_builder_at_benchmark_scale():
     for w in range(5):
         assert np.array_equal(h.section(w), g.section(w)), w
     del g2
+
+
+def test_rows_beyond_2_pow_32():
+    """SURVEY.md section 8 size table: KILT-scale indexes need 33-bit rows ("ranges must be u64",
+    /root/reference/seal/cpp_modules/fm_index.hpp:16-18).  A closed-form index with size() = 2^32 + 5 000: the text
+    a^n $ has SA[i] = n - i and BWT = a^n $, so every answer is known without building anything: rank counters above
+    2^32, LF steps, locate (a walk of up to 31 LF steps ending on a 33-bit SA sample), document ids by bisection."""
+    from seal_b200.cpp_modules.fm_index import FMIndex as RawFM
+    from seal_b200._lib import lib, check
+    n = (1 << 32) + 4999
+    m = n + 1
+    words = (m + 63) // 64
+    tree = np.full(words, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    tree[n >> 6] = np.uint64((1 << (n & 63)) - 1)          # bit n (the sentinel's row) and the padding are 0
+    tree[(n >> 6) + 1:] = 0
+    sa = (np.uint64(n) - np.arange((m + 31) // 32, dtype=np.uint64) * np.uint64(32))
+    isa = (np.uint64(n) - np.arange(n // 64 + 1, dtype=np.uint64) * np.uint64(64))
+    fm = RawFM.from_sections(m, 1, tree, [0, 1], [0, 1, m], sa, isa)
+    del tree, sa, isa
+    fm.to_device(0)
+    assert fm.size() == m
+    beginnings = np.arange(0, n + 1000, 1000, dtype=np.uint64)
+    check(lib.sealfm_set_beginnings(fm._handle(), beginnings.ctypes.data, len(beginnings)))
+    rng = np.random.default_rng(3)
+    big = (1 << 32)
+    l = np.concatenate([rng.integers(big - 100, n - 10, size=500), rng.integers(0, n - 10, size=500)]).astype(np.uint64)
+    r = np.minimum(l + rng.integers(0, 5000, size=1000).astype(np.uint64), np.uint64(n))      # inclusive, may include the sentinel row
+    ol, oh = fm.backward_search_step_batch(np.ones(1000, dtype=np.uint64), l, r)
+    assert np.array_equal(ol, 1 + np.minimum(l, n)) and np.array_equal(oh, np.minimum(r + 1, n).astype(np.uint64))
+    assert int(ol.max()) > big and int(oh.max()) > big
+    # 'aaa' has n - 2 occurrences; its range is [3, n + 1) -- 33-bit bounds out of backward_search_multi
+    lo, hi = fm.backward_search_multi([1, 1, 1])
+    assert (lo, hi) == (3, n + 1)
+    rows = np.concatenate([rng.integers(big, m, size=2000), rng.integers(0, m, size=2000), [0, n, m, big - 1, big, big + 1]]).astype(np.uint64)
+    pos = fm.locate_batch(rows)
+    exp = np.where(rows < m, np.uint64(n) - np.minimum(rows, np.uint64(n)), np.uint64(0xFFFFFFFFFFFFFFFF))
+    assert np.array_equal(pos, exp)
+    ok = rows < m
+    docs = np.zeros(int(ok.sum()), dtype=np.uint64)
+    rr = np.ascontiguousarray(rows[ok])
+    check(lib.sealfm_doc_index_from_rows(fm._dev(), len(rr), rr.ctypes.data, docs.ctypes.data))
+    assert np.array_equal(docs, (np.searchsorted(beginnings, exp[ok], side="right") - 1).astype(np.uint64))
+    # successor sets through the expansion kernels: a range inside the a-run -> {a}; one that ends on the last row -> {a, $}
+    out = fm.distinct_count_multi([big + 5, n - 3], [big + 5000, n + 1])
+    assert out[0] == [1, 4995] and out[1] == [0, 1, 1, 3]
