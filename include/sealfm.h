@@ -47,8 +47,9 @@ int         sealfm_abi_version(void);
 int sealfm_build(const uint64_t* symbols, uint64_t n, sealfm_t** out);
 /* Same index as sealfm_build (identical sections, byte for byte), constructed on CUDA device `device`:
  * radix-sort prefix doubling -> BWT -> level-wise wavelet tree -> samples (replaces sdsl::construct_im's
- * qsufsort + wt_int construction, sdsl/construct.hpp:120-166, sdsl/wt_int.hpp:169-256).  n + 1 < 2^31;
- * larger texts: sealfm_build.  SEALFM_ENODEVICE without a GPU. */
+ * qsufsort + wt_int construction, sdsl/construct.hpp:120-166, sdsl/wt_int.hpp:169-256).  n + 1 < 2^32 (32-bit
+ * ranks) and ~40 bytes of free device memory per symbol (SEALFM_ENOMEM otherwise); larger texts: sealfm_build.
+ * SEALFM_ENODEVICE without a GPU. */
 int sealfm_build_gpu(const uint64_t* symbols, uint64_t n, int device, sealfm_t** out);
 /* Adopts index sections computed elsewhere -- exactly what sealfm_section() hands out of a built index: the
  * level-concatenated wavelet-tree bits of csa_wt_int<> (sdsl/wt_int.hpp:202-242; size * max_level bits in n_tree

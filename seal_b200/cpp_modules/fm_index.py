@@ -38,13 +38,17 @@ def _default_device():
 
 
 def _build_on_gpu(n):
-    """Index construction runs on the GPU (sealfm_build_gpu) whenever one is visible and the text fits its
-    32-bit ranks; SEALB200_BUILD=host selects the host SA-IS builder (the only one without a GPU)."""
-    if os.environ.get("SEALB200_BUILD", "gpu") == "host" or n + 1 >= (1 << 31) - 8:
+    """Index construction runs on the GPU (sealfm_build_gpu) whenever one is visible, the text fits its 32-bit ranks
+    (n + 1 < 2^32) and ~40 bytes per symbol of device memory are free; SEALB200_BUILD=host selects the host SA-IS
+    builder (the only one without a GPU)."""
+    if os.environ.get("SEALB200_BUILD", "gpu") == "host" or n + 1 >= (1 << 32) - 8:
         return False
     try:
         import torch
-        return torch.cuda.is_available()
+        if not torch.cuda.is_available():
+            return False
+        free_b, _ = torch.cuda.mem_get_info(_default_device())
+        return (n + 1) * 42 + (1 << 30) <= free_b
     except Exception:
         return False
 

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "pdl.cuh"
+
 namespace sealb200 {
 
 constexpr int kHeadDim = 64;
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
                                                        const float* __restrict__ pos_table,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ out, SplitOut so) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -140,10 +143,14 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
 }
 
 // out[r] = LN(a[r] + b[r])     (residual + sub-layer output, post-LN)
+// With k_slices > 1, b is the raw split-K output of the preceding GEMM: b[r] = (sum_s part[s][r]) * unscale + bias, the
+// slices summed in index order (what umma_splitk_finish_kernel computes) -- the finish pass is folded into this kernel.
 __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                      const float* __restrict__ b, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ out,
-                                                     SplitOut so) {
+                                                     SplitOut so, int k_slices, int64_t slice_stride,
+                                                     const float* __restrict__ bias, float unscale) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -153,7 +160,15 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
     for (int i = 0; i < kLnMaxVec; ++i) if (i < nv) {
         const int col = (i * 32 + lane) * 4;
         const float4 x = *reinterpret_cast<const float4*>(a + r * d + col);
-        const float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
+        float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
+        if (k_slices > 1) {
+            for (int sl = 1; sl < k_slices; ++sl) {
+                const float4 p = *reinterpret_cast<const float4*>(b + sl * slice_stride + r * d + col);
+                y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+            }
+            const float4 bb = *reinterpret_cast<const float4*>(bias + col);
+            y.x = y.x * unscale + bb.x; y.y = y.y * unscale + bb.y; y.z = y.z * unscale + bb.z; y.w = y.w * unscale + bb.w;
+        }
         v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
     }
     warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out, so, r * d, lane);
@@ -380,6 +395,7 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
                                                                const float* __restrict__ qkv, float* kc, float* vc,
                                                                const int32_t* __restrict__ anc,
                                                                float* __restrict__ out, SplitOut so, int row_mul, int bcast) {
+    pdl_enter();
     // row_mul / bcast: at the first decode step all beams of a query are the same row (same start token, same
     // source), so the step runs on one row per query: compact row r stands for physical rows r*row_mul ..
     // r*row_mul + bcast - 1, whose cache entries all receive this row's k / v (any of them may become the
@@ -429,6 +445,7 @@ __global__ void __launch_bounds__(512) dec_self_attn_long_kernel(int64_t R, int 
                                                                  const float* __restrict__ qkv, float* kc, float* vc,
                                                                  const int32_t* __restrict__ anc,
                                                                  float* __restrict__ out, SplitOut so) {
+    pdl_enter();
     __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -549,6 +566,7 @@ __global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G,
                                                          const int32_t* __restrict__ grp_query,
                                                          const int32_t* __restrict__ grp_start, float* __restrict__ out,
                                                          SplitOut so, const int32_t* __restrict__ src_off) {
+    pdl_enter();
     // src_off (packed sources): query qi's encoder states are rows src_off[qi] .. src_off[qi+1] of ckv, all valid
     const int64_t gi = blockIdx.x;
     const int h = blockIdx.y;
@@ -575,6 +593,7 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
                                                                const int32_t* __restrict__ grp_query,
                                                                const int32_t* __restrict__ grp_start, float* __restrict__ out,
                                                                SplitOut so, const int32_t* __restrict__ src_off) {
+    pdl_enter();
     __shared__ __align__(16) float Ks[kXKeys][kXPad];
     __shared__ __align__(16) float Vs[kXKeys][kHeadDim];
     __shared__ __align__(16) float Qs[kXRows][kHeadDim];

@@ -11,7 +11,9 @@
 // Device-wide radix sort and prefix sum are CUB's (CUDA toolkit primitives, like cuBLAS for a plain
 // GEMM); everything specific to the index is written here.  Memory: 40 bytes per symbol.
 //
-// Limit: m < 2^31 (32-bit ranks, 64-bit keys).  Larger texts (NQ / KILT scale) go through the host builder.
+// Limit: m < 2^32 (32-bit ranks and positions, 64-bit keys, 64-bit item counts in the CUB calls) AND 40 B x m of free
+// device memory: ~4.2e9 symbols on a 180 GB B200, i.e. an NQ-sized text (~3.2e9) fits, a KILT-sized one (~5.5e9, 33-bit
+// rows) does not -- that one goes through the host SA-IS builder; the query kernels are 64-bit throughout.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -115,7 +117,14 @@ inline uint32_t hi_bit64(uint64_t x) { uint32_t r = 0; while (x >>= 1) ++r; retu
 void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex& o) {
     o = HostIndex();
     const uint64_t m = n + 1;
-    if (m >= (1ULL << 31) - 8) throw ApiError(SEALFM_EINVAL, "GPU index construction handles texts below 2^31 symbols; use sealfm_build");
+    if (m >= (1ULL << 32) - 8) throw ApiError(SEALFM_EINVAL, "GPU index construction handles texts below 2^32 symbols (32-bit ranks); use sealfm_build");
+    {
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        if ((double)m * 42.0 + (double)(1ull << 30) > (double)free_b)
+            throw ApiError(SEALFM_ENOMEM, "GPU index construction needs ~40 bytes of device memory per symbol; use sealfm_build");
+    }
     std::vector<uint32_t> text(m);
     for (uint64_t i = 0; i < n; ++i) {
         if (symbols[i] == 0) throw ApiError(SEALFM_EINVAL, "symbol 0 is reserved for the sentinel");
@@ -132,10 +141,10 @@ void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex&
 
     // one temp buffer big enough for every CUB call below
     size_t tmp_sort64 = 0, tmp_sort32 = 0, tmp_scan = 0, tmp_keys32 = 0;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort64, d_key_a.p, d_key_b.p, d_pos_a.p, d_pos_b.p, (int)m, 0, 64, st));
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort32, d_flag.p, d_grp.p, d_pos_a.p, d_pos_b.p, (int)m, 0, 32, st));
-    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_keys32, d_flag.p, d_grp.p, (int)m, 0, 32, st));
-    CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, d_flag.p, d_grp.p, (int)m, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort64, d_key_a.p, d_key_b.p, d_pos_a.p, d_pos_b.p, (int64_t)m, 0, 64, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort32, d_flag.p, d_grp.p, d_pos_a.p, d_pos_b.p, (int64_t)m, 0, 32, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_keys32, d_flag.p, d_grp.p, (int64_t)m, 0, 32, st));
+    CUDA_CHECK(cub::DeviceScan::InclusiveSum(nullptr, tmp_scan, d_flag.p, d_grp.p, (int64_t)m, st));
     const size_t tmp_bytes = std::max(std::max(tmp_sort64, tmp_sort32), std::max(tmp_scan, tmp_keys32));
     Dev<uint8_t> d_tmp(tmp_bytes);
     size_t tb;
@@ -144,7 +153,7 @@ void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex&
     auto rerank = [&](auto* sorted_key, const uint32_t* sorted_pos) -> uint32_t {
         boundary_kernel<<<G, kBT, 0, st>>>(sorted_key, d_flag.p, m);
         tb = tmp_bytes;
-        CUDA_CHECK(cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_flag.p, d_grp.p, (int)m, st));
+        CUDA_CHECK(cub::DeviceScan::InclusiveSum(d_tmp.p, tb, d_flag.p, d_grp.p, (int64_t)m, st));
         scatter_rank_kernel<<<G, kBT, 0, st>>>(sorted_pos, d_grp.p, d_rank.p, m);
         CUDA_CHECK(cudaGetLastError());
         uint32_t groups = 0;
@@ -158,7 +167,7 @@ void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex&
     const int sym_bits = (int)hi_bit64(std::max<uint32_t>(1, *std::max_element(text.begin(), text.end()))) + 1;
     uint32_t* d_sym_sorted = reinterpret_cast<uint32_t*>(d_key_b.p);           // scratch: key_b is free in round 0
     tb = tmp_bytes;
-    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_text.p, d_sym_sorted, d_pos_a.p, d_pos_b.p, (int)m, 0, sym_bits, st));
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_text.p, d_sym_sorted, d_pos_a.p, d_pos_b.p, (int64_t)m, 0, sym_bits, st));
     uint32_t groups = rerank(d_sym_sorted, d_pos_b.p);
     o.size = m;
     o.sigma = groups;
@@ -180,7 +189,7 @@ void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex&
     for (uint64_t h = 1; groups < m; h <<= 1) {
         pair_key_kernel<<<G, kBT, 0, st>>>(d_rank.p, d_key_a.p, d_pos_a.p, m, h);
         tb = tmp_bytes;
-        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key_a.p, d_key_b.p, d_pos_a.p, d_pos_b.p, (int)m, 0, 32 + rank_bits, st));
+        CUDA_CHECK(cub::DeviceRadixSort::SortPairs(d_tmp.p, tb, d_key_a.p, d_key_b.p, d_pos_a.p, d_pos_b.p, (int64_t)m, 0, 32 + rank_bits, st));
         groups = rerank(d_key_b.p, d_pos_b.p);
         if (h > m) throw ApiError(SEALFM_ECUDA, "suffix sort did not converge");
     }
@@ -209,7 +218,7 @@ void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex&
     for (uint32_t k = 0; k < L; ++k) {
         if (k > 0) {                                                            // order by the k leading bits
             tb = tmp_bytes;
-            CUDA_CHECK(cub::DeviceRadixSort::SortKeys(d_tmp.p, tb, cur, nxt, (int)m, (int)(L - k), (int)L, st));
+            CUDA_CHECK(cub::DeviceRadixSort::SortKeys(d_tmp.p, tb, cur, nxt, (int64_t)m, (int)(L - k), (int)L, st));
             // always re-sort from the BWT order: radix sort on bits [L-k, L) is stable, so this IS the node order
             pack_level_kernel<<<PG, kBT, 0, st>>>(nxt, reinterpret_cast<uint32_t*>(d_tree.p), m, k, L);
         } else {

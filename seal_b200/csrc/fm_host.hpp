@@ -25,7 +25,7 @@ struct HostIndex {
 // All throw std::runtime_error with a message on failure.
 void build_index(const uint64_t* symbols, uint64_t n, HostIndex& out);
 void build_index_from_file(const std::string& path, int width_bytes, HostIndex& out);
-// Same result as build_index, constructed on CUDA device `device` (fm_build.cu); n + 1 < 2^31.
+// Same result as build_index, constructed on CUDA device `device` (fm_build.cu); n + 1 < 2^32 and 40 B x n of free device memory.
 void build_index_gpu(const uint64_t* symbols, uint64_t n, int device, HostIndex& out);
 void load_index(const std::string& path, HostIndex& out);        // sdsl .fmi or native, auto-detect
 void save_index_native(const HostIndex& idx, const std::string& path);

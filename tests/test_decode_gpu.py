@@ -442,3 +442,23 @@ def test_fm_index_generate_keep_history_false(kw):
         seq_exp = fm_index_generate_oracle(model, ora, ids, am, keep_history=False, transformers_output=True, **kw)
         seq_got = fm_index_generate(model, idx, ids, am, transformers_output=True, **kw)
         assert torch.equal(seq_got.cpu(), seq_exp)
+
+
+def test_batch20_graph_replay_bart_large_is_bit_stable():
+    """The reference's operating point through the host-buffer API, three times: eager, captured, replayed (CUDA graph
+    with programmatic dependent launches between the ~1 900 kernels) -- all three must return identical records."""
+    from oracle.decode_oracle import make_bart
+    from seal_b200._lib import lib
+    from seal_b200.beam_search import SealBartEngine, generate_records
+    from seal_b200.index import FMIndex
+    from seal_b200.synthetic import make_corpus, make_queries
+    docs = make_corpus(n_docs=2000, doc_len=100, n_phrases=4000, seed=21)
+    idx = FMIndex(); idx.initialize([d.tolist() for d in docs], in_memory=True)
+    eng = SealBartEngine.from_hf(make_bart(seed=0), device=0)
+    ids, am = make_queries(20, seed=77)
+    kw = dict(num_beams=15, min_length=10, max_length=10, length_penalty=0.0)
+    recs = [generate_records(eng, idx, ids, am, **kw) for _ in range(4)]
+    assert int(lib.sealbart_get_stat(eng._h, b"last_used_graph")) == 1
+    for r in recs[1:]:
+        for k in ("scores", "lens", "tokens", "valid", "lo", "hi"):
+            assert np.array_equal(r[k], recs[0][k]), k

@@ -275,5 +275,5 @@ def test_rows_beyond_2_pow_32():
     check(lib.sealfm_doc_index_from_rows(fm._dev(), len(rr), rr.ctypes.data, docs.ctypes.data))
     assert np.array_equal(docs, (np.searchsorted(beginnings, exp[ok], side="right") - 1).astype(np.uint64))
     # successor sets through the expansion kernels: a range inside the a-run -> {a}; one that ends on the last row -> {a, $}
-    out = fm.distinct_count_multi([big + 5, n - 3], [big + 5000, n + 1])
-    assert out[0] == [1, 4995] and out[1] == [0, 1, 1, 3]
+    out = fm.distinct_count_multi([big + 5, n - 3, big + 5], [big + 4000, n + 1, n + 1])
+    assert out[0] == [1, 3995] and out[1] == [0, 1, 1, 3] and out[2] == [0, 1, 1, 4994]

@@ -70,3 +70,15 @@ def test_gemm_throughput_report():
         for mode in (0, 1, 2, 3, 4, 5):
             _, us = run_gemm(mode, A, W, b, False, iters=5)
             print(f"GEMM {M}x{N}x{K} mode {mode}: {us:.1f} us, {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (fp32-equivalent)")
+
+
+def test_gemm_small_m_report():
+    """Latency of the skinny-problem path (batch 20 x beam 15 = 300 decoder rows; 125 queries per GPU under strong
+    scaling = 1 875 rows): 128 x 64 tiles in one launch (umma_gemm_skinny.cuh) vs round 1's split-K + finish kernel
+    (SEALB200_SKINNY=0 restores it for an A/B)."""
+    rng = np.random.default_rng(0)
+    for (M, N, K) in [(300, 3072, 1024), (300, 1024, 1024), (300, 4096, 1024), (300, 1024, 4096), (1875, 1024, 1024), (1875, 1024, 4096)]:
+        A = rng.standard_normal((M, K)).astype(np.float32); W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
+        b = np.zeros(N, dtype=np.float32)
+        _, us = run_gemm(5, A, W, b, False, iters=50)
+        print(f"GEMM {M}x{N}x{K} mode 5: {us:.1f} us per call (launches back to back)")

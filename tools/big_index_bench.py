@@ -22,6 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from seal_b200.synthetic import make_corpus, make_queries, VOCAB  # noqa: E402
 
+TITLE_EOS = 49314          # '@@' in BART's vocabulary: SEALSearcher.title_eos_token_id
+
 
 def cuda_time(fn, iters=10, warmup=3):
     for _ in range(warmup):
@@ -48,12 +50,17 @@ def main():
     base = make_corpus()                                      # [100 000, 100] int32
     reps = max(1, args.tokens // base.size)
     rng = np.random.Generator(np.random.PCG64(2024))
-    docs = np.empty((reps * base.shape[0], base.shape[1]), dtype=np.int32)
+    # documents in SEAL's title form (scripts/build_fm_index.py:132): title tokens, the title separator, body, </s> --
+    # the first 6 tokens of every synthetic document act as its title
+    docs = np.empty((reps * base.shape[0], base.shape[1] + 1), dtype=np.int32)
     for r in range(reps):
         perm = np.arange(VOCAB, dtype=np.int32)
         if r:
             perm[4:] = rng.permutation(VOCAB - 4).astype(np.int32) + 4      # specials (0..3) stay
-        docs[r * base.shape[0]:(r + 1) * base.shape[0]] = perm[base]
+        blk = perm[base]
+        blk[blk == TITLE_EOS] = TITLE_EOS - 1                           # the separator only ever separates
+        d = docs[r * base.shape[0]:(r + 1) * base.shape[0]]
+        d[:, :6] = blk[:, :6]; d[:, 6] = TITLE_EOS; d[:, 7:] = blk[:, 6:]
     out["corpus_s"] = time.time() - t
     n = docs.size
     out["tokens"] = int(n)
@@ -73,10 +80,11 @@ def main():
 
     # ---- properties instead of an oracle -----------------------------------------------------------------------
     flat = docs.reshape(-1)
+    DL = docs.shape[1]
     checks = []
     prng = np.random.default_rng(5)
     for _ in range(6):
-        d = int(prng.integers(0, docs.shape[0])); a = int(prng.integers(0, 90)); L = int(prng.integers(1, 5))
+        d = int(prng.integers(0, docs.shape[0])); a = int(prng.integers(7, 90)); L = int(prng.integers(1, 5))
         gram = docs[d, a:a + L]
         lo, hi = index.get_range(gram.tolist())
         # brute force over the text: occurrences inside one document (the index text is per-document reversed, so an
@@ -85,7 +93,7 @@ def main():
         for k in range(L):
             hit &= flat[k:n - L + 1 + k] == gram[k]
         starts = np.nonzero(hit)[0]
-        starts = starts[(starts % 100) + L <= 100]
+        starts = starts[(starts % DL) + L <= DL]
         ok_count = (hi - lo) == len(starts)
         # fold of single steps == multi
         l, r = 0, m
@@ -95,7 +103,7 @@ def main():
         # located rows are occurrences: positions are in reversed-text coordinates -> document id must hold the n-gram
         rows = np.arange(lo, min(hi, lo + 64), dtype=np.uint64)
         pos, doc_ids = index.locate_rows(rows)
-        ok_loc = all(any((docs[int(di), j:j + L] == gram).all() for j in range(0, 100 - L + 1)) for di in doc_ids.tolist())
+        ok_loc = all(any((docs[int(di), j:j + L] == gram).all() for j in range(0, DL - L + 1)) for di in doc_ids.tolist())
         checks.append({"len": L, "count": int(hi - lo), "brute": int(len(starts)), "count_ok": bool(ok_count), "fold_ok": bool(ok_fold), "locate_ok": bool(ok_loc)})
     out["property_checks"] = checks
     out["properties_ok"] = all(c["count_ok"] and c["fold_ok"] and c["locate_ok"] for c in checks)
@@ -130,11 +138,27 @@ def main():
     # ---- decode on the big index -------------------------------------------------------------------------------
     if not args.no_decode:
         from bench import make_model
+        from seal_b200._lib import lib
         from seal_b200.beam_search import SealBartEngine, generate_records
         index.occurring_distinct, index.occurring_counts = index.get_distinct_count(0, len(index))
         model = make_model()
         eng = SealBartEngine.from_hf(model, device=0)
         del model
+        # BASELINE.json configs[4] shape: batch 64, beam 15, title pass (seal/retrieval.py:161-175: min 1 / max 15, decoding
+        # forced to start after a </s>, own end-of-title token) followed by the body pass -- 14 + 9 decode steps
+        ids64, am64 = make_queries(64, seed=99)
+        title_kw = dict(min_length=1, max_length=15, length_penalty=0.0, num_beams=15, forced_bos_token_id=None,
+                        force_decoding_from=[2], eos_token_id=TITLE_EOS)
+        body_kw = dict(min_length=10, max_length=10, length_penalty=0.0, num_beams=15, forced_bos_token_id=None)
+        for _ in range(3):
+            generate_records(eng, index, ids64, am64, **title_kw); generate_records(eng, index, ids64, am64, **body_kw)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(5):
+            rt = generate_records(eng, index, ids64, am64, **title_kw); rb = generate_records(eng, index, ids64, am64, **body_kw)
+        dt = (time.perf_counter() - t0) / 5
+        n_titles = int(((rt["valid"] == 1) & (rt["tokens"][np.arange(64)[:, None], np.arange(rt["lens"].shape[1])[None, :], np.maximum(rt["lens"] - 1, 0)] == TITLE_EOS)).sum())
+        out["decode_title_plus_body_Q64"] = {"ms_per_batch": dt * 1e3, "queries_per_s": 64 / dt, "complete_titles_found": n_titles,
+                                             "used_cuda_graph": int(lib.sealbart_get_stat(eng._h, b"last_used_graph"))}
         for Q in (20, 1000):
             ids, am = make_queries(Q, seed=4321)
             kw = dict(min_length=10, max_length=10, length_penalty=0.0, num_beams=15, forced_bos_token_id=None)
