@@ -369,9 +369,21 @@ def rank_kernel_report(index, full, dev, hbm, phases, args):
             hi2 = lo2 + torch.randint(1, big.size() // 2, (Nlf,), device=dev, generator=g)
             s2 = time_lf(big, sy, lo2, hi2)
             gbs = Nlf * 768 / s2 / 1e9
+            # the memory system's ceiling for this access pattern: independent random 32-byte sector reads over a buffer of
+            # the index's size (sealfm_debug_sector_probe); an LF step reads 2 such sectors per tree level
+            import ctypes as C
+            from seal_b200._lib import lib, check
+            us = C.c_double(0)
+            n_loads = Nlf * 32
+            check(lib.sealfm_debug_sector_probe(int(big.device_bytes()), n_loads, 5, C.byref(us)))
+            ceil_sectors = n_loads / (us.value * 1e-6)
+            lf_sectors = Nlf * 32 / s2
             out["hbm_index"] = {"index_tokens": n_big, "device_bytes": int(big.device_bytes()), "triples": Nlf, "us": s2 * 1e6,
                                 "algorithmic_GBps": gbs, "hbm_peak_GBps": hbm, "frac_of_hbm_peak": gbs / hbm,
-                                "bound": "HBM, random 32-byte sectors (index 5x the L2)"}
+                                "sector_GBps": lf_sectors * 32 / 1e9, "random_sector_ceiling_GBps": ceil_sectors * 32 / 1e9,
+                                "frac_of_random_sector_ceiling": lf_sectors / ceil_sectors,
+                                "bound": "HBM, random 32-byte sectors (index 5x the L2): the copy peak is not reachable with 32-byte "
+                                         "random accesses, the measured ceiling of that pattern is random_sector_ceiling_GBps"}
             del big
         except Exception as ex:  # pragma: no cover
             out["hbm_index"] = {"error": repr(ex)}

@@ -60,6 +60,7 @@ _FM_SIGS = {
     "sealfm_extract_text": (i32, [vp, u64, vp, vp, vp, vp, u64]),
     "sealfm_backward_search_step_d": (i32, [vp, vp, u64, vp, vp, vp, vp, vp]),
     "sealfm_expand_mask_d": (i32, [vp, vp, u64, vp, vp, vp, u32, u32, u32]),
+    "sealfm_debug_sector_probe": (i32, [u64, u64, i32, C.POINTER(C.c_double)]),
 }
 
 

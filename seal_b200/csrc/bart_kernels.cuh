@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
                                                        const float* __restrict__ pos_table,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        float* __restrict__ out, SplitOut so) {
-    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -150,7 +149,6 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
                                                      const float* __restrict__ beta, float* __restrict__ out,
                                                      SplitOut so, int k_slices, int64_t slice_stride,
                                                      const float* __restrict__ bias, float unscale) {
-    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -395,7 +393,6 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
                                                                const float* __restrict__ qkv, float* kc, float* vc,
                                                                const int32_t* __restrict__ anc,
                                                                float* __restrict__ out, SplitOut so, int row_mul, int bcast) {
-    pdl_enter();
     // row_mul / bcast: at the first decode step all beams of a query are the same row (same start token, same
     // source), so the step runs on one row per query: compact row r stands for physical rows r*row_mul ..
     // r*row_mul + bcast - 1, whose cache entries all receive this row's k / v (any of them may become the
@@ -445,7 +442,6 @@ __global__ void __launch_bounds__(512) dec_self_attn_long_kernel(int64_t R, int 
                                                                  const float* __restrict__ qkv, float* kc, float* vc,
                                                                  const int32_t* __restrict__ anc,
                                                                  float* __restrict__ out, SplitOut so) {
-    pdl_enter();
     __shared__ __align__(16) float q_s[16][kHeadDim];
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -566,7 +562,6 @@ __global__ void __launch_bounds__(kGAttnWarps * 32) cross_attn_kernel(int64_t G,
                                                          const int32_t* __restrict__ grp_query,
                                                          const int32_t* __restrict__ grp_start, float* __restrict__ out,
                                                          SplitOut so, const int32_t* __restrict__ src_off) {
-    pdl_enter();
     // src_off (packed sources): query qi's encoder states are rows src_off[qi] .. src_off[qi+1] of ckv, all valid
     const int64_t gi = blockIdx.x;
     const int h = blockIdx.y;
@@ -593,7 +588,6 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
                                                                const int32_t* __restrict__ grp_query,
                                                                const int32_t* __restrict__ grp_start, float* __restrict__ out,
                                                                SplitOut so, const int32_t* __restrict__ src_off) {
-    pdl_enter();
     __shared__ __align__(16) float Ks[kXKeys][kXPad];
     __shared__ __align__(16) float Vs[kXKeys][kHeadDim];
     __shared__ __align__(16) float Qs[kXRows][kHeadDim];

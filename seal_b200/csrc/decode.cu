@@ -7,7 +7,6 @@
 #include "fm_handle.hpp"
 #include "umma_gemm.cuh"
 #include "umma_gemm_2cta.cuh"
-#include "umma_gemm_skinny.cuh"
 
 #include <cuda_runtime.h>
 
@@ -30,7 +29,6 @@ struct Lin {
     float w_unscale = 1.f;                                 // 2^-s
     CUtensorMap map_hi{}, map_lo{}; bool maps_ready = false;
     CUtensorMap map2_hi{}, map2_lo{}; bool maps2_ready = false;   // 128-row boxes: one CTA's half of a pair's W tile (gemm_mode 5)
-    CUtensorMap map3_hi{}, map3_lo{}; bool maps3_ready = false;   // 64-row boxes: the skinny kernel's W tile
 };
 struct LNp { float* g = nullptr; float* b = nullptr; };
 struct EncLayerW { Lin qkv, o, fc1, fc2; LNp ln_attn, ln_final; };
@@ -300,43 +298,6 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             if (force_slices > 0) k_slices = std::min(force_slices, kblocks);     // experiments only
             while (k_slices > 1 && kblocks % k_slices) --k_slices;
         }
-        // skinny problems: 128 x 64 tiles, whole-K per tile, bias / GELU / split in the GEMM's own epilogue
-        // (umma_gemm_skinny.cuh); K is sliced only where a tile's K loop alone is long (fc2, K = 4096)
-        static const bool skinny_on = [] { const char* e = std::getenv("SEALB200_SKINNY"); return !e || std::atoi(e) != 0; }();
-        if (skinny_on && rowb == 128 && tiles * 2 <= sm_count()) {
-            if (!l.maps3_ready) { make_map(&l.map3_hi, l.w_h1, N, K, K, SK_BN, true, 128); make_map(&l.map3_lo, l.w_h2, N, K, K, SK_BN, true, 128); l.maps3_ready = true; }
-            const int m_tiles = (int)((M + UM - 1) / UM), n_tiles = (N + SK_BN - 1) / SK_BN;
-            const int items = m_tiles * n_tiles, nk = K / 64;
-            int ks = 1;
-            if (nk > 16) {
-                ks = std::min(8, std::max(1, 2 * sm_count() / items));
-                while (ks > 1 && (nk % ks || nk / ks < 4)) --ks;
-            }
-            const int ctas_sk = std::min(items * ks, sm_count());
-            auto launch_sk = [&](auto kern, const float* b, float unscale, float* out, __half* o1, __half* o2, int64_t stride) {
-                CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
-                launch_pdl(kern, ctas_sk, SK_THREADS, SK_SMEM, cx.s, ma1, ma2, l.map3_hi, l.map3_lo, (int)M, N, K, b, unscale, out, o1, o2, ldc, ovf, ks, stride);
-                m->launches++;
-            };
-            if (ks == 1) {
-                if (gelu) launch_sk(umma_gemm_f16x3_skinny_kernel<true>, l.b, l.w_unscale, C.x, C.h1, C.h2, 0);
-                else launch_sk(umma_gemm_f16x3_skinny_kernel<false>, l.b, l.w_unscale, C.x, C.h1, C.h2, 0);
-                return;
-            }
-            const int64_t slice_stride = (int64_t)M * ldc;
-            m->splitk.ensure((size_t)ks * slice_stride * 4);
-            float* part = m->splitk.as<float>();
-            launch_sk(umma_gemm_f16x3_skinny_kernel<false>, nullptr, 1.0f, part, nullptr, nullptr, slice_stride);
-            if (cx.defer_ok && !gelu && !C.h1 && !C.hi && ldc == N && l.b) {     // the caller's add_ln sums the slices
-                cx.pending = PendingSplit{part, ks, slice_stride, l.b, l.w_unscale};
-                return;
-            }
-            const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
-            if (gelu) launch_pdl(umma_splitk_finish_kernel<true>, fblocks, 256, 0, cx.s, M, N, ldc, ks, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
-            else launch_pdl(umma_splitk_finish_kernel<false>, fblocks, 256, 0, cx.s, M, N, ldc, ks, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
-            m->launches++;
-            return;
-        }
         if (m->cfg.gemm_mode == 5 && k_slices == 1 && M > UM) {
             // CTA pairs (cluster of 2, tcgen05.mma.cta_group::2) on 256 x 256 tiles: a third less operand
             // traffic out of L2 per MMA than the one-CTA kernel (umma_gemm_2cta.cuh)
@@ -359,7 +320,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             if (tail_s > 1) { m->splitk.ensure((size_t)(pair_tiles - full_items) * tail_s * 65536 * 4); part = m->splitk.as<float>(); }
             auto launchp = [&](auto kern) {
                 CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM));
-                launch_pdl(kern, 2 * pairs, UTHREADS2, U2_SMEM, cx.s, ma1, ma2, l.map2_hi, l.map2_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf,
+                launch_k(kern, 2 * pairs, UTHREADS2, U2_SMEM, cx.s, ma1, ma2, l.map2_hi, l.map2_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf,
                            full_items, tail_s, part);
             };
             if (gelu) launchp(umma_gemm_f16x3_2cta_kernel<true>); else launchp(umma_gemm_f16x3_2cta_kernel<false>);
@@ -367,8 +328,8 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             if (tail_s > 1) {
                 const int fb = (pair_tiles - full_items) * 64;
                 const int pm_tiles = (m_tiles + 1) / 2;
-                if (gelu) launch_pdl(umma_tail_finish_kernel<true>, fb, 256, 0, cx.s, (int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
-                else launch_pdl(umma_tail_finish_kernel<false>, fb, 256, 0, cx.s, (int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+                if (gelu) launch_k(umma_tail_finish_kernel<true>, fb, 256, 0, cx.s, (int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+                else launch_k(umma_tail_finish_kernel<false>, fb, 256, 0, cx.s, (int)M, N, ldc, n_tiles, pm_tiles, n_fastest, full_items, tail_s, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
                 CUDA_CHECK(cudaGetLastError()); m->launches++;
             }
             return;
@@ -380,21 +341,25 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             const int ctas2 = std::min(tiles * k_slices, sm_count());
             auto launch2 = [&](auto kern) {
                 CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
-                launch_pdl(kern, ctas2, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, nullptr, 1.0f, part, nullptr, nullptr,
+                launch_k(kern, ctas2, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, nullptr, 1.0f, part, nullptr, nullptr,
                            ldc, n_fastest, ovf, k_slices, slice_stride);
             };
             if (rowb == 128) launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
             else launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
+            if (cx.defer_ok && !gelu && !C.h1 && !C.hi && ldc == N && l.b) {     // the caller's add+LN sums the slices itself
+                cx.pending = PendingSplit{part, k_slices, slice_stride, l.b, l.w_unscale};
+                return;
+            }
             const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
-            if (gelu) launch_pdl(umma_splitk_finish_kernel<true>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
-            else launch_pdl(umma_splitk_finish_kernel<false>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+            if (gelu) launch_k(umma_splitk_finish_kernel<true>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
+            else launch_k(umma_splitk_finish_kernel<false>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
             return;
         }
         auto launch = [&](auto kern) {
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
-            launch_pdl(kern, ctas, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf, 1, (int64_t)0);
+            launch_k(kern, ctas, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf, 1, (int64_t)0);
         };
         if (rowb == 128) { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>); }
         else { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 64>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>); }
@@ -427,7 +392,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
     const PendingSplit ps = cx.pending;
     cx.pending = PendingSplit{};
-    launch_pdl(add_ln_kernel, (unsigned)((rows + 3) / 4), 128, 0, cx.s, rows, d, a, ps.ks > 1 ? ps.part : b, (const float*)ln.g, (const float*)ln.b, out.x,
+    launch_k(add_ln_kernel, (unsigned)((rows + 3) / 4), 128, 0, cx.s, rows, d, a, ps.ks > 1 ? ps.part : b, (const float*)ln.g, (const float*)ln.b, out.x,
                split_of(out, cx.m->ovf), ps.ks > 1 ? ps.ks : 1, ps.stride, ps.bias, ps.unscale);
     cx.m->launches++;
 }
@@ -592,7 +557,9 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
         gemm(cx, Te, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf), soff);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
+        cx.defer_ok = true;
         gemm(cx, Te, d, d, attn, d, L.o, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, Te, d, x.x, tmp.x, L.ln_attn, x);
         gemm(cx, Te, D.f, d, x, d, L.fc1, ffn, D.f, true);
         cx.defer_ok = true;
@@ -635,7 +602,7 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     const Act cq{m->dcq.as<float>()};
     const Act ffn = mk(m->dffn.as<float>(), m->dffn_hi, m->dffn_lo, false);
     const float scale = m->cfg.scale_embedding ? sqrtf((float)d) : 1.0f;
-    launch_pdl(embed_ln_kernel, (unsigned)((R + 3) / 4), 128, 0, cx.s, R, d, tokens + pos, (int64_t)(D.T * row_mul), (const int32_t*)nullptr, pos,
+    launch_k(embed_ln_kernel, (unsigned)((R + 3) / 4), 128, 0, cx.s, R, d, tokens + pos, (int64_t)(D.T * row_mul), (const int32_t*)nullptr, pos,
                (const float*)m->shared, scale, (const float*)m->dec_pos, (const float*)m->dec_ln_emb.g, (const float*)m->dec_ln_emb.b, x.x, split_of(x, ovf));
     m->launches++;
     const int heads = m->cfg.heads;
@@ -647,26 +614,30 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         const unsigned sa_threads = 32 * std::min(heads, 16);
         if (pos + 1 <= 12)
-            launch_pdl(dec_self_attn_kernel<3>, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf), row_mul, row_mul);
+            launch_k(dec_self_attn_kernel<3>, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf), row_mul, row_mul);
         else if (pos + 1 <= 32)
-            launch_pdl(dec_self_attn_kernel<8>, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf), row_mul, row_mul);
+            launch_k(dec_self_attn_kernel<8>, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf), row_mul, row_mul);
         else
-            launch_pdl(dec_self_attn_long_kernel, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf));
+            launch_k(dec_self_attn_long_kernel, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf));
         m->launches++;
+        cx.defer_ok = true;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
         const int64_t groups = D.grp_start ? D.G : D.Q;
         const float* ckv_l = m->ckv.as<float>() + (size_t)l * Tk * 2 * d;
         const int32_t* soff_x = m->enc_packed ? m->src_off.as<int32_t>() : nullptr;
         if (D.S <= kXKeys)
-            launch_pdl(cross_attn_small_kernel, dim3((unsigned)groups, heads), 128, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
+            launch_k(cross_attn_small_kernel, dim3((unsigned)groups, heads), 128, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
                        ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x);
         else
-            launch_pdl(cross_attn_kernel, dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
+            launch_k(cross_attn_kernel, dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
                        ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x);
         m->launches++;
+        cx.defer_ok = true;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
         gemm(cx, R, D.f, d, x, d, L.fc1, ffn, D.f, true);
         cx.defer_ok = true;
@@ -795,7 +766,7 @@ int sealbart_finalize(sealbart_t* m) {
             for (void* p : m->split_allocs) cudaFree(p);
             m->split_allocs.clear();
             m->tf32_ready = false;
-            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; l.maps3_ready = false; });
+            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; });
             unsigned int* d_max = nullptr;
             if (m->cfg.gemm_mode >= 3) { CUDA_CHECK(cudaMalloc(&d_max, 4)); m->err.ensure(16); CUDA_CHECK(cudaMemset(m->err.p, 0, 16)); }
             auto split_lin_half = [&](Lin& l) {
@@ -929,11 +900,11 @@ void generate_enqueue(Ctx& cx, const Dims& D, const GenArgs& a, const FmView& vi
         st.hyp_lo = a.o_lo; st.hyp_hi = a.o_hi; st.error_flag = a.err_d;
         // first step: beams 1.. carry -1e9 and are pruned exactly inside one CTA per query; afterwards one CTA per row
         if (cur_len == 1) {
-            launch_pdl(topk_rows_kernel<512, 8192>, (unsigned)Q, 512, sizeof(RowsFirst), cx.s, c, st, rs, 1, B);
-            launch_pdl(select_merge_kernel, (unsigned)Q, kMergeThreads, 0, cx.s, view, c, st, rs, 1);
+            launch_k(topk_rows_kernel<512, 8192>, (unsigned)Q, 512, sizeof(RowsFirst), cx.s, c, st, rs, 1, B);
+            launch_k(select_merge_kernel, (unsigned)Q, kMergeThreads, 0, cx.s, view, c, st, rs, 1);
         } else {
-            launch_pdl(topk_rows_kernel<256, 4096>, (unsigned)R, 256, sizeof(RowsLater), cx.s, c, st, rs, B, 1);
-            launch_pdl(select_merge_kernel, (unsigned)Q, kMergeThreads, 0, cx.s, view, c, st, rs, B);
+            launch_k(topk_rows_kernel<256, 4096>, (unsigned)R, 256, sizeof(RowsLater), cx.s, c, st, rs, B, 1);
+            launch_k(select_merge_kernel, (unsigned)Q, kMergeThreads, 0, cx.s, view, c, st, rs, B);
         }
         m->launches += 2;
         if (c.expand_next && !p->disable_fm_index) {           // successor sets of the new beams -> next step's masks (:107)
@@ -1099,7 +1070,7 @@ int sealbart_set_option(sealbart_t* m, const char* name, int64_t value) {
             if (value == 2 && m->cfg.gemm_mode >= 3) { ensure_tf32_splits(m); m->cfg.gemm_mode = 2; }
             else if (value >= 3 && value <= 5 && m->head.w_h1) m->cfg.gemm_mode = (int)value;
             else throw ApiError(SEALFM_EINVAL, "gemm_mode can only switch between the 3xFP16 modes (3, 4, 5) and 2 (3xTF32)");
-            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; l.maps3_ready = false; });
+            for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; });
             drop_graphs(m);
         }
         else throw ApiError(SEALFM_EINVAL, "unknown option: " + n);

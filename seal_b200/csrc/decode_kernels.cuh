@@ -163,7 +163,6 @@ struct RowScratch {
 // the constrained scores restricted to the group (:302-307) -- exact: the query's top-K is the top-K of its groups' top-Ks.
 template <int THREADS, int BUF>
 __global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 2 : 4) topk_rows_kernel(StepCfg c, StepState st, RowScratch rs, int groups, int rows_per_cta) {
-    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using SH = SelSharedT<BUF>;
     SH& S = *reinterpret_cast<SH*>(smem_raw);
@@ -334,7 +333,6 @@ struct MergeShared {
 // (incremental get_range) of every record and new beam.  The successor sets of the new beams (next step's masks)
 // are expanded by the FM-index kernels right after (fm_kernels.cu launch_expand_masks), over all rows of the batch.
 __global__ void __launch_bounds__(kMergeThreads) select_merge_kernel(FmView fm, StepCfg c, StepState st, RowScratch rs, int groups) {
-    pdl_enter();
     __shared__ MergeShared S;
     const int B = c.num_beams, K = c.K, V = c.V;
     const int64_t qi = blockIdx.x;

@@ -220,6 +220,22 @@ __global__ void __launch_bounds__(256) order_pairs_kernel(uint32_t present_words
     if (threadIdx.x == 0) out_len[r] = 2ull * k;
 }
 
+// Measurement aid (sealfm_debug_sector_probe): independent random 32-byte sector reads over a buffer, four in flight
+// per thread -- the memory system's ceiling for the access pattern of a rank query, the denominator the LF kernel's
+// beyond-L2 rate is compared with (a streaming-copy peak is not reachable with 32-byte random accesses).
+__global__ void __launch_bounds__(256) sector_probe_kernel(const uint4* __restrict__ buf, uint64_t n_sectors, uint64_t n_loads,
+                                                           uint64_t seed, unsigned long long* __restrict__ sink) {
+    auto mix = [](uint64_t x) { x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); };
+    uint32_t acc = 0;
+    for (uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 4; t < n_loads; t += (uint64_t)gridDim.x * blockDim.x * 4) {
+        const uint64_t i0 = mix(t + seed) % n_sectors, i1 = mix(t + 1 + seed) % n_sectors, i2 = mix(t + 2 + seed) % n_sectors, i3 = mix(t + 3 + seed) % n_sectors;
+        const uint4 a0 = __ldg(buf + 2 * i0), b0 = __ldg(buf + 2 * i0 + 1), a1 = __ldg(buf + 2 * i1), b1 = __ldg(buf + 2 * i1 + 1);
+        const uint4 a2 = __ldg(buf + 2 * i2), b2 = __ldg(buf + 2 * i2 + 1), a3 = __ldg(buf + 2 * i3), b3 = __ldg(buf + 2 * i3 + 1);
+        acc ^= a0.x ^ b0.w ^ a1.y ^ b1.z ^ a2.z ^ b2.y ^ a3.w ^ b3.x;
+    }
+    if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ULL);              // keeps the loads alive
+}
+
 __global__ void __launch_bounds__(128) locate_kernel(FmView v, uint64_t n, const uint64_t* __restrict__ rows,
                                                      uint64_t* __restrict__ out, int want_doc) {
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -620,7 +636,8 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             const uint64_t cn = c1 - c0, pairs = ub[c1] - ub[c0];
             std::vector<uint64_t> off(cn + 1);
             for (uint64_t i = 0; i <= cn; ++i) off[i] = ub[c0 + i] - ub[c0];
-            const size_t zero_bytes = (cn * 4 + 15) / 16 * 16 + (size_t)cn * words * 4 + (cn + 2) * 8;
+            const size_t cnt_bytes = (cn * 4 + 15) / 16 * 16, present_bytes = ((size_t)cn * words * 4 + 15) / 16 * 16;     // 16-byte aligned regions
+            const size_t zero_bytes = cnt_bytes + present_bytes + (cn + 2) * 8;
             Stage st(h, (2 * cn + cn + 1 + 2 * pairs + cn) * 8 + zero_bytes + 256, true);
             const uint64_t* dlo = (const uint64_t*)st.put(lows + c0, cn * 8);
             const uint64_t* dhi = (const uint64_t*)st.put(highs + c0, cn * 8);
@@ -630,8 +647,8 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             char* z = (char*)st.reserve(zero_bytes);
             st.zero(z, zero_bytes);
             unsigned int* dcnt = (unsigned int*)z;
-            uint32_t* dpresent = (uint32_t*)(z + (cn * 4 + 15) / 16 * 16);
-            unsigned long long* dwide = (unsigned long long*)(z + (cn * 4 + 15) / 16 * 16 + (size_t)cn * words * 4);
+            uint32_t* dpresent = (uint32_t*)(z + cnt_bytes);
+            unsigned long long* dwide = (unsigned long long*)(z + cnt_bytes + present_bytes);
             const PairRows rows{dlist, doff, dcnt, dpresent, words};
             expand_rows_kernel<PairRows><<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32, ns, st.stream()>>>(h->view, cn, dlo, dhi, rows, dwide);
             CUDA_CHECK(cudaGetLastError());
@@ -699,6 +716,31 @@ int sealfm_extract_text(const sealfm_t* h, uint64_t n, const uint64_t* begins, c
         CUDA_CHECK(cudaGetLastError());
         st.get(out, dout, tot * 8);
         st.sync();
+    });
+}
+
+/* Measurement aid: `n_loads` independent random 32-byte sector reads over a zero-filled device buffer of `buffer_bytes`
+ * (4 in flight per thread); average device time per pass over `iters` passes (CUDA events). */
+int sealfm_debug_sector_probe(uint64_t buffer_bytes, uint64_t n_loads, int iters, double* avg_us) {
+    return guarded([&] {
+        if (!avg_us || buffer_bytes < 64 || !n_loads || iters < 1) throw ApiError(SEALFM_EINVAL, "bad argument");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); throw ApiError(SEALFM_ENODEVICE, "no CUDA device available"); }
+        DevBuf<uint8_t> buf(buffer_bytes);
+        DevBuf<unsigned long long> sink(1);
+        CUDA_CHECK(cudaMemset(buf.p, 0, buffer_bytes));
+        CUDA_CHECK(cudaMemset(sink.p, 0, 8));
+        const uint64_t n_sectors = buffer_bytes / 32;
+        const int grid = sm_count() * 8;
+        sector_probe_kernel<<<grid, 256>>>((const uint4*)buf.p, n_sectors, n_loads, 1, sink.p);
+        cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaEventRecord(e0));
+        for (int i = 0; i < iters; ++i) sector_probe_kernel<<<grid, 256>>>((const uint4*)buf.p, n_sectors, n_loads, 7919ull * (i + 2), sink.p);
+        CUDA_CHECK(cudaEventRecord(e1));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        *avg_us = (double)ms * 1e3 / iters;
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
     });
 }
 

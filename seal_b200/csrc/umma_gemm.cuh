@@ -547,7 +547,6 @@ umma_gemm_f16x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, co
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
     if (threadIdx.x == 0) gemm_trace(1);
-    pdl_enter();                                               // barriers / TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
         if (lane == 0) {
@@ -707,7 +706,6 @@ __global__ void __launch_bounds__(256) umma_splitk_finish_kernel(int64_t M, int 
                                                                  const float* __restrict__ part, const float* __restrict__ bias,
                                                                  float w_unscale, float* __restrict__ C, __half* __restrict__ C_h1,
                                                                  __half* __restrict__ C_h2, int* __restrict__ overflow) {
-    pdl_enter();
     const int64_t total = M * (int64_t)(ldc / 4);
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = e / (ldc / 4);

@@ -117,7 +117,6 @@ umma_gemm_f16x3_2cta_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
-    pdl_enter();                                                // barriers / TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
         if (lane == 0) {
@@ -281,7 +280,6 @@ __global__ void __launch_bounds__(256) umma_tail_finish_kernel(int M, int N, int
                                                                int full_items, int tail_s, const float* __restrict__ part,
                                                                const float* __restrict__ bias, float w_unscale, float* __restrict__ C,
                                                                __half* __restrict__ C_h1, __half* __restrict__ C_h2, int* __restrict__ overflow) {
-    pdl_enter();
     const int t = blockIdx.x >> 6;                                // tail tile; 64 blocks of 256 threads x float4 each
     const int e = ((blockIdx.x & 63) << 8) + threadIdx.x;
     const int lr = e >> 6, c4 = e & 63;

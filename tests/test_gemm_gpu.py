@@ -73,9 +73,8 @@ def test_gemm_throughput_report():
 
 
 def test_gemm_small_m_report():
-    """Latency of the skinny-problem path (batch 20 x beam 15 = 300 decoder rows; 125 queries per GPU under strong
-    scaling = 1 875 rows): 128 x 64 tiles in one launch (umma_gemm_skinny.cuh) vs round 1's split-K + finish kernel
-    (SEALB200_SKINNY=0 restores it for an A/B)."""
+    """Latency of the small-problem path (batch 20 x beam 15 = 300 decoder rows; 125 queries per GPU under strong
+    scaling = 1 875 rows): split-K over up to 8 CTAs per 128 x 256 tile + finish pass (a record, not an assertion)."""
     rng = np.random.default_rng(0)
     for (M, N, K) in [(300, 3072, 1024), (300, 1024, 1024), (300, 4096, 1024), (300, 1024, 4096), (1875, 1024, 1024), (1875, 1024, 4096)]:
         A = rng.standard_normal((M, K)).astype(np.float32); W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
