@@ -489,7 +489,6 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
     m->st_rowmax.ensure(D.R * 4); m->st_rowls.ensure(D.R * 4); m->st_rule.ensure(D.R);
     m->st_cval.ensure((size_t)D.R * 2 * D.B * 4); m->st_cidx.ensure((size_t)D.R * 2 * D.B * 4); m->st_ccnt.ensure(D.R * 4);
-    m->st_wide.ensure((D.R + 2) * 8);
     if (m->cfg.gemm_mode >= 1) {
         m->ex_hi.ensure(Tk * D.d * 4); m->ex_lo.ensure(Tk * D.d * 4);
         m->eattn_hi.ensure(Tk * D.d * 4); m->eattn_lo.ensure(Tk * D.d * 4);
@@ -972,6 +971,7 @@ int sealdec_generate_dx(sealbart_t* m, const sealfm_t* fm, const uint32_t* occ_d
         m->last_used_graph = 0;
         const Dims D = make_dims(m, Q, S, B, T);
         ensure_workspace(m, D);
+        if (!p->disable_fm_index) m->st_wide.ensure(expand_scratch_bytes(view.L, (uint64_t)D.R));   // wide-row work list + BFS frontiers
         const GenArgs a{fm, occ_d, p, ids_d, mask_d, Q, S, o_score, o_len, o_tok, o_valid, o_lo, o_hi, err_d};
 
         // ---- CUDA graph of the whole call: a batch-20 generate is ~1 900 short kernels, i.e. launch-latency-bound.

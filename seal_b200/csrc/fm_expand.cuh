@@ -145,11 +145,7 @@ __device__ void warp_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sin
 
 
 
-// Block-cooperative expansion for WIDE ranges (thousands of distinct successors): the warp version
-// leaves one warp walking tens of thousands of tree nodes (measured tail: 3.5 ms for one row).  Here a
-// whole CTA expands one range: level-synchronous frontier in shared memory with atomic (unordered)
-// child append until there are at least two sub-trees per thread (or the buffer is full), then every
-// thread walks its sub-trees depth-first.  Sinks must be order-independent (bitmask OR / appended pairs).
+// Shared-memory frontier of the block-cooperative expansion of WIDE ranges (block_expand_bfs below).
 template <int CAP>
 struct BlockFrontierT {
     static constexpr int kCap = CAP;
@@ -157,27 +153,47 @@ struct BlockFrontierT {
     uint64_t j[2][CAP];
     uint32_t prefix[2][CAP];
     int count[2];
-    int next;                       // work-queue cursor of the depth-first phase
 };
-using BlockFrontier = BlockFrontierT<1024>;   // 40 KB (+ 80 KB of depth-first stack for 256 threads): two CTAs per SM
+using BlockFrontier = BlockFrontierT<1024>;   // 40 KB: five 256-thread CTAs per SM
 constexpr uint64_t kWideRange = 2048;       // ranges at least this wide go to the block path
 
-// stk_i / stk_j: kMaxLevels x blockDim.x u64 each (shared memory) for the depth-first phase.
+
+// Level-synchronous expansion of one WIDE range by a whole CTA -- no depth-first phase, no per-thread stack: the
+// frontier of level l (at most 2^l nodes, (i, j, prefix) each) lives in shared memory while it fits and in this CTA's
+// global scratch (two buffers of 2^(L-1) entries; L2-resident) beyond that; every thread takes frontier entries in a
+// strided loop, so a range with thousands of distinct successors keeps all 256 threads on independent rank queries
+// at every level (the depth-first hand-out left threads walking sub-trees of very different sizes, and its stacks
+// capped the occupancy at 512 threads per SM).  Children of the last level go straight to the sink.
+// Visits exactly the nodes wt_int::_interval_symbols visits (sdsl/wt_int.hpp:108-147); order-independent sinks only.
+struct GlobalFrontier {
+    uint64_t* i; uint64_t* j; uint32_t* prefix;      // [2][cap] each
+    uint32_t cap;                                    // entries per buffer (>= 2^(L-1))
+};
+__host__ __device__ inline size_t global_frontier_bytes(uint32_t L) { return (size_t)2 * ((size_t)1 << (L - 1)) * 20; }
+
 template <typename Sink, typename Frontier>
-__device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, Frontier& F, uint64_t* stk_i, uint64_t* stk_j) {
+__device__ void block_expand_bfs(const FmView& v, uint64_t lo, uint64_t hi, Sink& sink, Frontier& F, const GlobalFrontier& G) {
     if (lo >= hi) return;                                      // uniform
     const int tid = threadIdx.x, nt = blockDim.x;
     const uint32_t L = v.L;
     __syncthreads();
-    if (tid == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; F.count[0] = 1; F.count[1] = 0; F.next = 0; }
+    if (tid == 0) { F.i[0][0] = lo; F.j[0][0] = hi; F.prefix[0][0] = 0; F.count[0] = 1; F.count[1] = 0; }
     __syncthreads();
     int cur = 0, n = 1;
-    uint32_t level = 0;
-    while (level < L && 2 * n <= Frontier::kCap) {             // as many sub-trees as the buffer holds
+    bool cur_global = false;
+    for (uint32_t level = 0; level < L; ++level) {
         const int nxt = cur ^ 1;
+        const bool last = level + 1 == L;
+        const bool nxt_global = !last && 2 * n > Frontier::kCap;          // uniform: an upper bound on the children
+        const uint64_t* ci = cur_global ? G.i + (size_t)cur * G.cap : F.i[cur];
+        const uint64_t* cj = cur_global ? G.j + (size_t)cur * G.cap : F.j[cur];
+        const uint32_t* cp = cur_global ? G.prefix + (size_t)cur * G.cap : F.prefix[cur];
+        uint64_t* ni = nxt_global ? G.i + (size_t)nxt * G.cap : F.i[nxt];
+        uint64_t* nj = nxt_global ? G.j + (size_t)nxt * G.cap : F.j[nxt];
+        uint32_t* np = nxt_global ? G.prefix + (size_t)nxt * G.cap : F.prefix[nxt];
         for (int e = tid; e < n; e += nt) {
-            const uint64_t ei = F.i[cur][e], ej = F.j[cur][e];
-            const uint32_t ep = F.prefix[cur][e];
+            const uint64_t ei = ci[e], ej = cj[e];
+            const uint32_t ep = cp[e];
             const NodeEntry ne = load_node(v, (1u << level) + ep);
             uint64_t a, b;
             if (ej == ei + 1) {
@@ -188,25 +204,23 @@ __device__ void block_expand(const FmView& v, uint64_t lo, uint64_t hi, Sink& si
                 a = rank1(v, ne.base + ei) - ne.ones;
                 b = rank1(v, ne.base + ej) - ne.ones;
             }
-            const bool has1 = (b - a) != 0, has0 = ((ej - ei) - (b - a)) != 0;
-            const int nc = (has0 ? 1 : 0) + (has1 ? 1 : 0);
-            int w = atomicAdd(&F.count[nxt], nc);
-            if (has0) { F.i[nxt][w] = ei - a; F.j[nxt][w] = ej - b; F.prefix[nxt][w] = ep << 1; ++w; }
-            if (has1) { F.i[nxt][w] = a; F.j[nxt][w] = b; F.prefix[nxt][w] = (ep << 1) | 1u; }
+            const bool has1 = b != a, has0 = (ej - ei) != (b - a);
+            if (last) {
+                if (has0) sink(ep << 1, ei - a, ej - b);
+                if (has1) sink((ep << 1) | 1u, a, b);
+            } else {
+                const int nc = (has0 ? 1 : 0) + (has1 ? 1 : 0);
+                int w = atomicAdd(&F.count[nxt], nc);
+                if (has0) { ni[w] = ei - a; nj[w] = ej - b; np[w] = ep << 1; ++w; }
+                if (has1) { ni[w] = a; nj[w] = b; np[w] = (ep << 1) | 1u; }
+            }
         }
-        __syncthreads();
+        __syncthreads();                                       // (global frontier writes are block-visible after the barrier)
         n = F.count[nxt];
         __syncthreads();
-        if (tid == 0) F.count[cur] = 0;                        // becomes the next "next"
-        cur = nxt; ++level;
+        if (tid == 0) F.count[cur] = 0;
+        cur = nxt; cur_global = nxt_global;
         __syncthreads();
     }
-    // sub-tree sizes differ by orders of magnitude: threads pull sub-trees from a shared cursor
-    for (;;) {
-        const int e = atomicAdd(&F.next, 1);
-        if (e >= n) break;
-        expand_dfs_smem(v, level, F.prefix[cur][e], F.i[cur][e], F.j[cur][e], sink, stk_i, stk_j, nt, tid);
-    }
-    __syncthreads();
 }
 }  // namespace sealb200

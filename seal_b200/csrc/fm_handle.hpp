@@ -7,7 +7,8 @@
 
 namespace sealb200 {
 FmView sealfm_view(const sealfm_t* h);   // defined in fm_kernels.cu; throws ApiError if not on a device
-// allowed-token bitmask rows of R SA ranges (fm_kernels.cu); `wide` = R + 2 u64 of device scratch
+// allowed-token bitmask rows of R SA ranges (fm_kernels.cu); `wide` = expand_scratch_bytes(L, R) of device scratch
+size_t expand_scratch_bytes(uint32_t L, uint64_t R);
 void launch_expand_masks(const FmView& v, cudaStream_t s, uint64_t R, const uint64_t* lo_d, const uint64_t* hi_d, uint32_t* mask_d,
                          uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide);
 }

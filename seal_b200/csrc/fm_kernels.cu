@@ -114,7 +114,6 @@ constexpr int kWideThreads = 256;
 
 // dynamic shared memory of the two kernel shapes for a tree of height L
 size_t narrow_smem(uint32_t L) { return kExpandWarps * warp_expand_smem(L); }
-size_t wide_smem(uint32_t L) { return sizeof(BlockFrontier) + 2ull * L * kWideThreads * 8; }
 
 __device__ __forceinline__ WarpFrontier& warp_frontier(unsigned char* smem, uint32_t L, uint32_t warp, uint64_t*& stk) {
     unsigned char* base = smem + warp * warp_expand_smem(L);
@@ -158,15 +157,19 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_rows_kernel(FmView v
     }
 }
 
-// Persistent CTAs pull the wide rows found by expand_rows_kernel (no host sync).
+// Persistent CTAs pull the wide rows found by expand_rows_kernel (no host sync) and expand each level-synchronously
+// (block_expand_bfs); `scratch` = gridDim.x regions of global_frontier_bytes(L).
 template <typename Rows>
 __global__ void __launch_bounds__(kWideThreads) expand_rows_wide_kernel(FmView v, const uint64_t* __restrict__ lo,
                                                                        const uint64_t* __restrict__ hi, Rows rows,
-                                                                       unsigned long long* wide_list) {
-    extern __shared__ __align__(16) unsigned char wide_smem_raw[];
-    BlockFrontier& F = *reinterpret_cast<BlockFrontier*>(wide_smem_raw);
-    uint64_t* stk = reinterpret_cast<uint64_t*>(wide_smem_raw + sizeof(BlockFrontier));
+                                                                       unsigned long long* wide_list, unsigned char* scratch) {
+    __shared__ BlockFrontier F;
     __shared__ unsigned long long pick;
+    const uint32_t cap = 1u << (v.L - 1);
+    unsigned char* mine = scratch + (size_t)blockIdx.x * global_frontier_bytes(v.L);
+    GlobalFrontier G;
+    G.cap = cap;
+    G.i = reinterpret_cast<uint64_t*>(mine); G.j = G.i + 2 * (size_t)cap; G.prefix = reinterpret_cast<uint32_t*>(G.j + 2 * (size_t)cap);
     const unsigned long long n = wide_list[0];
     for (;;) {
         if (threadIdx.x == 0) pick = atomicAdd(wide_list + 1, 1ULL);
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kWideThreads) expand_rows_wide_kernel(FmView v
         if (k >= n) break;
         const uint64_t r = wide_list[2 + k];
         auto sink = rows.sink(r);
-        block_expand(v, lo[r], hi[r], sink, F, stk, stk + (size_t)v.L * kWideThreads);
+        block_expand_bfs(v, lo[r], hi[r], sink, F, G);
     }
 }
 
@@ -410,22 +413,30 @@ void release_device(sealfm_t* h) {
 }  // namespace
 
 namespace sealb200 {
+// CTAs of the wide kernel: four per SM, fewer when their global frontiers (2^(L-1) entries each) would pass 1 GB
+static int wide_ctas_for(uint64_t R, uint32_t L) {
+    const uint64_t by_mem = std::max<uint64_t>((uint64_t)sm_count() / 2, ((uint64_t)1 << 30) / global_frontier_bytes(L));
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(R, std::min<uint64_t>((uint64_t)sm_count() * 4, by_mem)));
+}
+// device scratch launch_expand_masks needs for R ranges on a tree of height L: the wide-row work list, then one global
+// frontier per wide CTA
+size_t expand_scratch_bytes(uint32_t L, uint64_t R) { return ((R + 2 + 1) / 2 * 2) * 8 + (size_t)wide_ctas_for(R, L) * global_frontier_bytes(L); }
+
 // Bitmask rows of R SA ranges: narrow ranges by one warp each, wide ones (>= kWideRange rows) by whole CTAs pulling
-// from a device-side work list.  `wide`: R + 2 u64 of scratch.  Stream-ordered, no host synchronisation; also the
-// tail of every decode step (decode.cu).
+// from a device-side work list.  `wide`: expand_scratch_bytes(L, R) of device scratch (work list + the wide CTAs' global
+// frontiers).  Stream-ordered, no host synchronisation; also the tail of every decode step (decode.cu).
 void launch_expand_masks(const FmView& v, cudaStream_t s, uint64_t R, const uint64_t* lo_d, const uint64_t* hi_d, uint32_t* mask_d,
                          uint32_t ld_words, uint32_t vocab, uint32_t shift, unsigned long long* wide) {
     if (v.L > kMaxLevels) throw ApiError(SEALFM_EINVAL, "wavelet tree higher than kMaxLevels");
     CUDA_CHECK(cudaMemsetAsync(wide, 0, 2 * sizeof(unsigned long long), s));
-    const int ns = (int)narrow_smem(v.L), ws = (int)wide_smem(v.L);
-    static int ns_set = 0, ws_set = 0;
+    const int ns = (int)narrow_smem(v.L);
+    static int ns_set = 0;
     if (ns > ns_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_rows_kernel<MaskRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ns)); ns_set = ns; }
-    if (ws > ws_set) { CUDA_CHECK(cudaFuncSetAttribute(expand_rows_wide_kernel<MaskRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws)); ws_set = ws; }
     const MaskRows rows{mask_d, ld_words, vocab, shift};
     expand_rows_kernel<MaskRows><<<grid_for(R, kExpandWarps, 16), kExpandWarps * 32, ns, s>>>(v, R, lo_d, hi_d, rows, wide);
     CUDA_CHECK(cudaGetLastError());
-    const int wide_ctas = (int)std::min<uint64_t>(R, (uint64_t)sm_count() * 2);
-    expand_rows_wide_kernel<MaskRows><<<wide_ctas, kWideThreads, ws, s>>>(v, lo_d, hi_d, rows, wide);
+    expand_rows_wide_kernel<MaskRows><<<wide_ctas_for(R, v.L), kWideThreads, 0, s>>>(v, lo_d, hi_d, rows, wide,
+                                                                              reinterpret_cast<unsigned char*>(wide + (R + 2 + 1) / 2 * 2));
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -566,7 +577,7 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, 
         if ((uint64_t)ld_words * 32 < vocab) throw ApiError(SEALFM_EINVAL, "ld_words too small for vocab");
         cudaStream_t s = (cudaStream_t)stream;
         unsigned long long* wide = nullptr;                    // [count, cursor, rows...]
-        CUDA_CHECK(cudaMallocAsync(&wide, (R + 2) * sizeof(unsigned long long), s));
+        CUDA_CHECK(cudaMallocAsync(&wide, expand_scratch_bytes(h->view.L, R), s));
         struct Free { unsigned long long* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{wide, s};
         launch_expand_masks(h->view, s, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);
     });
@@ -626,9 +637,8 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
         std::vector<uint64_t> lens(n, 0), tmp;
         out_offsets[0] = 0;
         const uint64_t kChunkPairs = 1ULL << 24;                // u64 of list scratch per pass (2 x 128 MB at most)
-        const int ns = (int)narrow_smem(L), ws = (int)wide_smem(L);
+        const int ns = (int)narrow_smem(L);
         CUDA_CHECK(cudaFuncSetAttribute(expand_rows_kernel<PairRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ns));
-        CUDA_CHECK(cudaFuncSetAttribute(expand_rows_wide_kernel<PairRows>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws));
         uint64_t written = 0;
         for (uint64_t c0 = 0; c0 < n;) {
             uint64_t c1 = c0 + 1;
@@ -637,8 +647,10 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             std::vector<uint64_t> off(cn + 1);
             for (uint64_t i = 0; i <= cn; ++i) off[i] = ub[c0 + i] - ub[c0];
             const size_t cnt_bytes = (cn * 4 + 15) / 16 * 16, present_bytes = ((size_t)cn * words * 4 + 15) / 16 * 16;     // 16-byte aligned regions
-            const size_t zero_bytes = cnt_bytes + present_bytes + (cn + 2) * 8;
-            Stage st(h, (2 * cn + cn + 1 + 2 * pairs + cn) * 8 + zero_bytes + 256, true);
+            const size_t wide_bytes = ((cn + 2 + 1) / 2 * 2) * 8;
+            const size_t zero_bytes = cnt_bytes + present_bytes + wide_bytes;
+            const size_t bfs_bytes = (size_t)wide_ctas_for(cn, L) * global_frontier_bytes(L);
+            Stage st(h, (2 * cn + cn + 1 + 2 * pairs + cn) * 8 + zero_bytes + bfs_bytes + 512, true);
             const uint64_t* dlo = (const uint64_t*)st.put(lows + c0, cn * 8);
             const uint64_t* dhi = (const uint64_t*)st.put(highs + c0, cn * 8);
             const uint64_t* doff = (const uint64_t*)st.put(off.data(), (cn + 1) * 8);
@@ -652,7 +664,8 @@ int sealfm_distinct_count_multi(const sealfm_t* h, uint64_t n, const uint64_t* l
             const PairRows rows{dlist, doff, dcnt, dpresent, words};
             expand_rows_kernel<PairRows><<<grid_for(cn, kExpandWarps, 16), kExpandWarps * 32, ns, st.stream()>>>(h->view, cn, dlo, dhi, rows, dwide);
             CUDA_CHECK(cudaGetLastError());
-            expand_rows_wide_kernel<PairRows><<<(int)std::min<uint64_t>(cn, (uint64_t)sm_count() * 2), kWideThreads, ws, st.stream()>>>(h->view, dlo, dhi, rows, dwide);
+            unsigned char* dbfs = (unsigned char*)st.reserve(bfs_bytes);
+            expand_rows_wide_kernel<PairRows><<<wide_ctas_for(cn, L), kWideThreads, 0, st.stream()>>>(h->view, dlo, dhi, rows, dwide, dbfs);
             CUDA_CHECK(cudaGetLastError());
             order_pairs_kernel<<<(unsigned)cn, 256, words * 4, st.stream()>>>(words, dpresent, dcnt, dlist, doff, dout, dlen);
             CUDA_CHECK(cudaGetLastError());
