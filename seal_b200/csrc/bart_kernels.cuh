@@ -142,13 +142,12 @@ __global__ void __launch_bounds__(128) embed_ln_kernel(int64_t rows, int d, cons
 }
 
 // out[r] = LN(a[r] + b[r])     (residual + sub-layer output, post-LN)
-// With k_slices > 1, b is the raw split-K output of the preceding GEMM: b[r] = (sum_s part[s][r]) * unscale + bias, the
-// slices summed in index order (what umma_splitk_finish_kernel computes) -- the finish pass is folded into this kernel.
+// (Round 2 tried folding the split-K finish pass of the preceding GEMM into this kernel: at 300 rows it has 75 CTAs and
+// became 21 us per launch against 6 + 3 us for the two separate kernels -- profiles/r02_c_launches_q20.csv -- reverted.)
 __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                      const float* __restrict__ b, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, float* __restrict__ out,
-                                                     SplitOut so, int k_slices, int64_t slice_stride,
-                                                     const float* __restrict__ bias, float unscale) {
+                                                     SplitOut so) {
     const int lane = threadIdx.x & 31;
     const int64_t r = blockIdx.x * 4LL + (threadIdx.x >> 5);
     if (r >= rows) return;
@@ -158,15 +157,7 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
     for (int i = 0; i < kLnMaxVec; ++i) if (i < nv) {
         const int col = (i * 32 + lane) * 4;
         const float4 x = *reinterpret_cast<const float4*>(a + r * d + col);
-        float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
-        if (k_slices > 1) {
-            for (int sl = 1; sl < k_slices; ++sl) {
-                const float4 p = *reinterpret_cast<const float4*>(b + sl * slice_stride + r * d + col);
-                y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
-            }
-            const float4 bb = *reinterpret_cast<const float4*>(bias + col);
-            y.x = y.x * unscale + bb.x; y.y = y.y * unscale + bb.y; y.z = y.z * unscale + bb.z; y.w = y.w * unscale + bb.w;
-        }
+        const float4 y = *reinterpret_cast<const float4*>(b + r * d + col);
         v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
     }
     warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out, so, r * d, lane);
@@ -424,6 +415,87 @@ __global__ void __launch_bounds__(512, ROUNDS <= 3 ? 2 : 1) dec_self_attn_kernel
                 *reinterpret_cast<float4*>(vd) = v0; *reinterpret_cast<float4*>(vd + 4) = v1;
             }
         }
+    }
+}
+
+// Decoder self-attention with the beams of a query processed TOGETHER (round 2).  The beams of a query share most of
+// their ancestors -- at position s the B rows point at only a few distinct cache rows -- but dec_self_attn_kernel gives
+// every row its own CTA and re-reads a shared ancestor's K / V once per beam (through L2; 1.36x the byte floor, and
+// bound by the number of L2 requests rather than by HBM).  Here one CTA per (query, head) first de-duplicates the
+// ancestor indices per position with warp match/ballot, stages each DISTINCT K / V head row (64 floats) once in shared
+// memory, then warp b attends for beam b out of shared memory.  Same arithmetic order per row as the other kernels is
+// not required (scores are summed per key in the same k order; softmax is the online form).
+// grid (Q, heads), block 32 * B threads, dynamic smem self_attn_query_smem(P, B).
+__host__ __device__ inline size_t self_attn_query_smem(int P, int B) { return (size_t)2 * P * B * kHeadDim * 4 + (size_t)2 * P * 32 * 4 + 128 * 4; }
+
+__global__ void __launch_bounds__(1024) dec_self_attn_query_kernel(int64_t R, int B, int d, int cur_pos, int T,
+                                                                  const float* __restrict__ qkv, float* kc, float* vc,
+                                                                  const int32_t* __restrict__ anc,
+                                                                  float* __restrict__ out, SplitOut so) {
+    extern __shared__ __align__(16) unsigned char sa_smem[];
+    const int P = cur_pos + 1;
+    float* Ks = reinterpret_cast<float*>(sa_smem);                       // [P][B][64]
+    float* Vs = Ks + (size_t)P * B * kHeadDim;
+    int32_t* row_of = reinterpret_cast<int32_t*>(Vs + (size_t)P * B * kHeadDim);   // [P][32] cache row of slot
+    int32_t* slot_of = row_of + P * 32;                                 // [P][32] slot of beam
+    int32_t* ucount = slot_of + P * 32;                                 // [P] (<= 128 positions)
+    const int64_t qi = blockIdx.x;
+    const int col = blockIdx.y * kHeadDim;
+    const int64_t r0 = qi * B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- 1. distinct ancestors per position
+    for (int s = warp; s < P; s += B) {
+        const bool act = lane < B;
+        const unsigned amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const int a = (s == cur_pos) ? lane : anc[(r0 + lane) * T + s];        // the current position: every beam has its own k / v
+            const unsigned same = __match_any_sync(amask, a);
+            const int leader = __ffs(same) - 1;
+            const unsigned leaders = __ballot_sync(amask, leader == lane);
+            slot_of[s * 32 + lane] = __popc(leaders & ((1u << leader) - 1u));
+            if (leader == lane) row_of[s * 32 + __popc(leaders & ((1u << lane) - 1u))] = a;
+            if (lane == 0) ucount[s] = __popc(leaders);
+        }
+    }
+    __syncthreads();
+    // ---- 2. stage the distinct K / V head rows once; persist the current position's k / v
+    const int per_pos = B * (kHeadDim / 4);
+    for (int e = threadIdx.x; e < P * per_pos; e += blockDim.x) {
+        const int s = e / per_pos, rem = e - s * per_pos, slot = rem / (kHeadDim / 4), i4 = rem - slot * (kHeadDim / 4);
+        if (slot >= ucount[s]) continue;
+        const int a = row_of[s * 32 + slot];
+        float4 kk, vv;
+        if (s == cur_pos) {
+            const float* qp = qkv + (r0 + a) * 3 * d + col + 4 * i4;
+            kk = __ldg(reinterpret_cast<const float4*>(qp + d)); vv = __ldg(reinterpret_cast<const float4*>(qp + 2 * d));
+            const int64_t off = ((int64_t)cur_pos * R + r0 + a) * d + col + 4 * i4;
+            *reinterpret_cast<float4*>(kc + off) = kk; *reinterpret_cast<float4*>(vc + off) = vv;
+        } else {
+            const int64_t off = ((int64_t)s * R + a) * d + col + 4 * i4;
+            kk = *reinterpret_cast<const float4*>(kc + off); vv = *reinterpret_cast<const float4*>(vc + off);
+        }
+        *reinterpret_cast<float4*>(Ks + ((size_t)s * B + slot) * kHeadDim + 4 * i4) = kk;
+        *reinterpret_cast<float4*>(Vs + ((size_t)s * B + slot) * kHeadDim + 4 * i4) = vv;
+    }
+    __syncthreads();
+    // ---- 3. warp b = beam b
+    if (warp < B) {
+        const int64_t r = r0 + warp;
+        const float2 q2 = __ldg(reinterpret_cast<const float2*>(qkv + r * 3 * d + col + 2 * lane));
+        float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
+        for (int s = 0; s < P; ++s) {
+            const int slot = slot_of[s * 32 + warp];
+            const float2 k2 = *reinterpret_cast<const float2*>(Ks + ((size_t)s * B + slot) * kHeadDim + 2 * lane);
+            const float sc = warp_sum(q2.x * k2.x + q2.y * k2.y) * 0.125f;
+            const float mn = fmaxf(m, sc);
+            const float corr = (m == -INFINITY) ? 0.f : expf(m - mn);
+            const float p = expf(sc - mn);
+            const float2 v2 = *reinterpret_cast<const float2*>(Vs + ((size_t)s * B + slot) * kHeadDim + 2 * lane);
+            l = l * corr + p;
+            ax = fmaf(p, v2.x, ax * corr); ay = fmaf(p, v2.y, ay * corr);
+            m = mn;
+        }
+        store_attn(make_float2(ax / l, ay / l), r * d + col + 2 * lane, out, so);
     }
 }
 

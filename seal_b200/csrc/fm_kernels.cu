@@ -576,7 +576,19 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R, 
         if (!R) return;
         if ((uint64_t)ld_words * 32 < vocab) throw ApiError(SEALFM_EINVAL, "ld_words too small for vocab");
         cudaStream_t s = (cudaStream_t)stream;
-        unsigned long long* wide = nullptr;                    // [count, cursor, rows...]
+        unsigned long long* wide = nullptr;                    // [count, cursor, rows...] + the wide CTAs' global frontiers
+        // the scratch is hundreds of MB for large R: keep freed blocks in the device's stream-ordered pool instead of
+        // returning them to the driver at every synchronisation (the default release threshold is 0)
+        static bool pool_kept = false;
+        if (!pool_kept) {
+            cudaMemPool_t pool = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess) {
+                uint64_t keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            pool_kept = true;
+        }
         CUDA_CHECK(cudaMallocAsync(&wide, expand_scratch_bytes(h->view.L, R), s));
         struct Free { unsigned long long* p; cudaStream_t s; ~Free() { cudaFreeAsync(p, s); } } guard{wide, s};
         launch_expand_masks(h->view, s, R, lo_d, hi_d, mask_d, ld_words, vocab, shift, wide);

@@ -123,145 +123,6 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 
 template <int BN, bool GELU>
 __global__ void __launch_bounds__(UTHREADS2, 1)
-umma_gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                        const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
-                        int M, int N, int K, const float* __restrict__ bias, float* __restrict__ C,
-                        float* __restrict__ C_hi, float* __restrict__ C_lo, int ldc) {
-    static_assert(BN == 256, "epilogue mapping assumes a 256-column tile (2 TMEM buffers = 512 columns)");
-    using SM = UmmaSmem<BN>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;          // SWIZZLE_128B wants 1024 B alignment
-    const uint32_t bars = base + USTAGES * SM::kStageBytes;
-    const uint32_t full0 = bars, empty0 = bars + 8 * USTAGES;             // smem stage barriers
-    const uint32_t tfull0 = bars + 16 * USTAGES, tempty0 = tfull0 + 16;   // 2 TMEM buffers
-    const uint32_t slot = tempty0 + 16;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.y, n_tile = blockIdx.x;
-    const int num_k = K / UK;
-    const int num_chunks = (num_k + UKC - 1) / UKC;
-
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < USTAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(tfull0 + 8 * b, 1); mbar_init(tempty0 + 8 * b, UEPI_WARPS); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    } else if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    uint32_t tmem_base;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
-
-    if (warp == 0) {
-        if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % USTAGES;
-                const uint32_t ph = (kb / USTAGES) & 1;
-                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                const uint32_t st = base + s * SM::kStageBytes;
-                mbar_expect_tx(full0 + 8 * s, SM::kStageBytes);
-                tma_load_2d(st, &tmA_hi, full0 + 8 * s, kb * UK, m_tile * UM);
-                tma_load_2d(st + SM::kABytes, &tmA_lo, full0 + 8 * s, kb * UK, m_tile * UM);
-                tma_load_2d(st + 2 * SM::kABytes, &tmW_hi, full0 + 8 * s, kb * UK, n_tile * BN);
-                tma_load_2d(st + 2 * SM::kABytes + SM::kWBytes, &tmW_lo, full0 + 8 * s, kb * UK, n_tile * BN);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor (cute/arch/mma_sm100_desc.hpp:InstrDescriptor): D=F32, A=B=TF32, K-major both,
-            // N>>3 at bit 17, M>>4 at bit 24
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(UM >> 4) << 24);
-            int kb = 0;
-            for (int c = 0; c < num_chunks; ++c) {
-                const int buf = c & 1;
-                mbar_wait(tempty0 + 8 * buf, ((c >> 1) & 1) ^ 1);     // epilogue has drained this buffer's previous use
-                tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(buf * BN);
-                const int kend = (kb + UKC < num_k) ? kb + UKC : num_k;
-                for (int k0 = kb; kb < kend; ++kb) {
-                    const int s = kb % USTAGES;
-                    const uint32_t ph = (kb / USTAGES) & 1;
-                    mbar_wait(full0 + 8 * s, ph);
-                    tc_fence_after();
-                    const uint32_t st = base + s * SM::kStageBytes;
-                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + SM::kABytes);
-                    const uint64_t w_hi = umma_desc_sw128(st + 2 * SM::kABytes), w_lo = umma_desc_sw128(st + 2 * SM::kABytes + SM::kWBytes);
-#pragma unroll
-                    for (int k = 0; k < UK / 8; ++k) {         // UMMA_K = 8 tf32 = 32 B -> +2 in the >>4 address field
-                        umma_tf32(tacc, a_lo + 2 * k, w_hi + 2 * k, idesc, (kb != k0) || (k != 0));
-                        umma_tf32(tacc, a_hi + 2 * k, w_lo + 2 * k, idesc, 1);
-                        umma_tf32(tacc, a_hi + 2 * k, w_hi + 2 * k, idesc, 1);
-                    }
-                    umma_commit(empty0 + 8 * s);               // frees the smem stage when these MMAs retire
-                }
-                umma_commit(tfull0 + 8 * buf);                 // this chunk's partial sums are complete
-            }
-        }
-    } else if (warp >= 4) {
-        const int q = warp & 3;                                // TMEM lane quarter this warp may touch (warp % 4)
-        const int cg = (warp - 4) >> 2;                        // column group: 64 columns
-        float acc[64];
-#pragma unroll
-        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
-        for (int c = 0; c < num_chunks; ++c) {
-            const int buf = c & 1;
-            mbar_wait(tfull0 + 8 * buf, (c >> 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + cg * 64 + h * 32), r);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) acc[h * 32 + j] += __uint_as_float(r[j]);      // round-to-nearest promotion
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
-        }
-        const int row = m_tile * UM + q * 32 + lane;
-        const int nb = n_tile * BN + cg * 64;
-        if (row < M && nb < N) {
-            const int64_t roff = (int64_t)row * ldc;
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                const int n = nb + j;
-                float v[4], vh[4], vl[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float x = acc[j + u] + ((bias && n + u < N) ? bias[n + u] : 0.f);
-                    v[u] = GELU ? gelu_erf_u(x) : x;
-                    vh[u] = __uint_as_float(__float_as_uint(v[u]) & 0xFFFFE000u);    // TF32 split for the next GEMM
-                    vl[u] = v[u] - vh[u];
-                }
-                if (n + 3 < N) {
-                    if (C) *reinterpret_cast<float4*>(C + roff + n) = make_float4(v[0], v[1], v[2], v[3]);
-                    if (C_hi) {
-                        *reinterpret_cast<float4*>(C_hi + roff + n) = make_float4(vh[0], vh[1], vh[2], vh[3]);
-                        *reinterpret_cast<float4*>(C_lo + roff + n) = make_float4(vl[0], vl[1], vl[2], vl[3]);
-                    }
-                } else {
-                    for (int u = 0; u < 4; ++u) if (n + u < N) {
-                        if (C) C[roff + n + u] = v[u];
-                        if (C_hi) { C_hi[roff + n + u] = vh[u]; C_lo[roff + n + u] = vl[u]; }
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
-
-// Persistent variant: one CTA per SM loops over output tiles, so the register-accumulator epilogue
-// (bias / GELU / TF32 split / global stores) of tile i overlaps the TMA+MMA main loop of tile i+1 and
-// there is no per-tile launch/TMEM-allocation tail.  Same arithmetic as the kernel above.
-template <int BN, bool GELU>
-__global__ void __launch_bounds__(UTHREADS2, 1)
 umma_gemm_tf32x3_persistent_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                         const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
                         int M, int N, int K, const float* __restrict__ bias, float* __restrict__ C,
