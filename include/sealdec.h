@@ -56,7 +56,7 @@ typedef struct {
     int32_t ffn_dim;           /* 4096                                         */
     int32_t max_positions;     /* 1024 (+2 learned offset)                     */
     int32_t scale_embedding;   /* 0 for bart-large                             */
-    int32_t gemm_mode;         /* 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = same with 64B rows / 4-stage pipeline, 5 = 3xFP16 on CTA pairs (cta_group::2, 256x256 tiles; mode 3's kernel for skinny problems) */
+    int32_t gemm_mode;         /* 5 = 3xFP16 on CTA pairs (cta_group::2, 256x256 tiles; mode 3's kernel with split-K for small problems; default), 3 = 3xFP16, one CTA per 128x256 tile, 2 = 3xTF32 (fp32 range).  All tcgen05 + TMA + TMEM. */
 } sealbart_config_t;
 
 int  sealbart_create(const sealbart_config_t* cfg, int device, sealbart_t** out);
@@ -147,7 +147,7 @@ int sealdec_generate_dx(sealbart_t* model, const sealfm_t* fm, const uint32_t* o
                         float* out_scores_d, int32_t* out_len_d, int32_t* out_tokens_d,
                         uint8_t* out_valid_d, uint64_t* out_lo_d, uint64_t* out_hi_d,
                         int32_t* error_flag_d, int64_t src_tokens_hint);
-/* Options: "cuda_graph" (-1 auto, 0 off, 1 on), "gemm_mode" (switch between the 3xFP16 modes 3/4/5 and 2 = 3xTF32;
+/* Options: "cuda_graph" (-1 auto, 0 off, 1 on), "gemm_mode" (switch between the 3xFP16 modes 3/5 and 2 = 3xTF32;
  * the TF32 operand copies are made on first use).  Stats: "last_used_graph", "overflow_fallbacks", "gemm_mode",
  * "cached_graphs" (-1 for an unknown name). */
 int     sealbart_set_option(sealbart_t* model, const char* name, int64_t value);
@@ -172,8 +172,8 @@ int sealdec_debug_step_logits(sealbart_t* model, const int64_t* input_ids, const
                               int64_t Q, int64_t S, int32_t num_beams, const int64_t* decoder_input_ids,
                               int64_t t, float* out_logits);
 /* Stand-alone GEMM C[M,N] = A[M,K] W[N,K]^T + bias (+GELU) through the model's GEMM kernels
- * (mode 0 = fp32 SIMT, 1 = 3xTF32 tcgen05, 2 = persistent 3xTF32, 3 = persistent 3xFP16, 4 = 3xFP16 4-stage), host pointers; if iters > 0 also reports the average
- * device time per call (CUDA events, includes the activation split in mode 1). */
+ * (mode 2 = 3xTF32, 3 = 3xFP16, 5 = 3xFP16 on CTA pairs), host pointers; if iters > 0 also reports the average
+ * device time per call (CUDA events, includes the activation split). */
 int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A, const float* W,
                        const float* bias, float* C, int32_t gelu, int32_t iters, double* avg_us);
 /* in-kernel timeline of CTA 0 of the mode-3/4 GEMM kernel (development aid): out20 (may be NULL) receives

@@ -139,7 +139,7 @@ int sealfm_expand_mask_d(const sealfm_t* h, sealfm_stream_t stream, uint64_t R,
                          uint32_t ld_words, uint32_t vocab, uint32_t shift);
 
 /* Measurement aid for the roofline of the rank kernels: average device time (us) of `n_loads` independent random 32-byte
- * sector reads over a device buffer of `buffer_bytes` (the access pattern of a rank query; 4 loads in flight per thread). */
+ * sector reads over a device buffer of `buffer_bytes` (the access pattern of a rank query; 8 loads in flight per thread). */
 int sealfm_debug_sector_probe(uint64_t buffer_bytes, uint64_t n_loads, int iters, double* avg_us);
 
 #ifdef __cplusplus

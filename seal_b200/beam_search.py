@@ -95,9 +95,8 @@ class SealBartEngine:
     """Device-resident BART weights + workspace (include/sealdec.h `sealbart_t`)."""
 
     def __init__(self, state_dict, config, device=0, gemm_mode=None):
-        # gemm_mode: 0 = fp32 SIMT, 1 = 3xTF32 tcgen05/TMA, 2 = persistent 3xTF32, 3 = persistent 3xFP16,
-        # 4 = 3 with 64-byte rows, 5 = 3xFP16 on CTA pairs (cta_group::2; default: fastest, same accuracy
-        # class; skinny problems use mode 3's split-K kernel).  $SEALB200_GEMM overrides the default.
+        # gemm_mode: 5 = 3xFP16 on CTA pairs (cta_group::2; default; small problems use mode 3's split-K kernel), 3 = 3xFP16 with
+        # one CTA per tile, 2 = 3xTF32 (fp32 range, the automatic fallback on fp16 overflow).  $SEALB200_GEMM overrides the default.
         if gemm_mode is None:
             gemm_mode = int(os.environ.get("SEALB200_GEMM", "5"))
         self.gemm_mode = int(gemm_mode)

@@ -163,92 +163,6 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
     warp_layernorm<kLnMaxVec>(v, nv, d, gamma, beta, 1e-5f, out, so, r * d, lane);
 }
 
-// ---- fp32 SIMT GEMM:  C[M,N] = A[M,K] * W[N,K]^T + bias[N]  (optionally GELU) ---------------------
-// A, W row-major with K contiguous (nn.Linear layout).  128x128x16 tiles, 256 threads, 8x8 per thread.
-constexpr int GBM = 128, GBN = 128, GBK = 16, GTHREADS = 256;
-
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-
-template <bool GELU>
-__global__ void __launch_bounds__(GTHREADS, 2) sgemm_tn_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                            const float* __restrict__ W, int ldw,
-                                                            const float* __restrict__ bias, float* __restrict__ C,
-                                                            int ldc) {
-    __shared__ __align__(16) float As[2][GBK][GBM + 4];
-    __shared__ __align__(16) float Bs[2][GBK][GBN + 4];
-    const int tid = threadIdx.x;
-    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-    // global -> smem mapping: each thread loads two float4 of A and two of W per k-tile
-    const int lrow = tid >> 2;            // 0..63
-    const int lk = (tid & 3) * 4;         // 0,4,8,12
-    float4 ra[2], rb[2];
-    auto gload = [&](int k0) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int am = m0 + lrow + 64 * h;
-            ra[h] = am < M ? *reinterpret_cast<const float4*>(A + (int64_t)am * lda + k0 + lk) : make_float4(0, 0, 0, 0);
-            const int bn = n0 + lrow + 64 * h;
-            rb[h] = bn < N ? *reinterpret_cast<const float4*>(W + (int64_t)bn * ldw + k0 + lk) : make_float4(0, 0, 0, 0);
-        }
-    };
-    auto sstore = [&](int buf) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int r = lrow + 64 * h;
-            As[buf][lk + 0][r] = ra[h].x; As[buf][lk + 1][r] = ra[h].y; As[buf][lk + 2][r] = ra[h].z; As[buf][lk + 3][r] = ra[h].w;
-            Bs[buf][lk + 0][r] = rb[h].x; Bs[buf][lk + 1][r] = rb[h].y; Bs[buf][lk + 2][r] = rb[h].z; Bs[buf][lk + 3][r] = rb[h].w;
-        }
-    };
-    const int ty = tid >> 4, tx = tid & 15;       // 16 x 16 thread grid, each 8x8 (two 4-wide halves)
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-
-    gload(0);
-    sstore(0);
-    __syncthreads();
-    const int nk = K / GBK;
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) gload((kt + 1) * GBK);
-#pragma unroll
-        for (int k = 0; k < GBK; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        if (kt + 1 < nk) sstore(buf ^ 1);
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-        if (m >= M) continue;
-#pragma unroll
-        for (int jh = 0; jh < 2; ++jh) {
-            const int nb = n0 + (jh ? 64 + tx * 4 : tx * 4);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int n = nb + j;
-                if (n < N) {
-                    float v = acc[i][jh * 4 + j] + (bias ? bias[n] : 0.f);
-                    if (GELU) v = gelu_erf(v);
-                    C[(int64_t)m * ldc + n] = v;
-                }
-            }
-        }
-    }
-}
-
 // ---- attention ---------------------------------------------------------------------------------
 // One warp per (row, head).  Scores: lane s owns key s (its own 256-byte K row against the query
 // staged in shared memory) -> two warp reductions per 32 keys instead of one per key; values: lane l

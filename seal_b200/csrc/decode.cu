@@ -24,7 +24,7 @@ namespace {
 
 struct Lin {
     float* w = nullptr; float* b = nullptr; int out = 0, in = 0;
-    float* w_hi = nullptr; float* w_lo = nullptr;          // TF32 split copies (gemm_mode 1, 2)
+    float* w_hi = nullptr; float* w_lo = nullptr;          // TF32 split copies (gemm_mode 2)
     __half* w_h1 = nullptr; __half* w_h2 = nullptr;        // FP16 split copies of W * 2^s (gemm_mode 3)
     float w_unscale = 1.f;                                 // 2^-s
     CUtensorMap map_hi{}, map_lo{}; bool maps_ready = false;
@@ -73,7 +73,7 @@ struct sealbart {
     Buf enc_tok, enc_mask, ex, eqkv, eattn, etmp, effn, ckv, src_off;
     bool enc_packed = false;          // the last encoder_forward ran on the real tokens only (src_off valid)
     Buf dx, dqkv, dattn, dtmp, dcq, dffn, logits, kc, vc;
-    Buf ex_hi, ex_lo, eattn_hi, eattn_lo, effn_hi, effn_lo, dx_hi, dx_lo, dattn_hi, dattn_lo, dffn_hi, dffn_lo;   // TF32 splits (gemm_mode 1)
+    Buf ex_hi, ex_lo, eattn_hi, eattn_lo, effn_hi, effn_lo, dx_hi, dx_lo, dattn_hi, dattn_lo, dffn_hi, dffn_lo;   // activation splits (halves or TF32)
     Buf st_scores, st_tokens, st_lo, st_hi, st_pw, st_anc, st_mask;
     Buf st_rowmax, st_rowls, st_rule, st_cval, st_cidx, st_ccnt, st_wide;     // scratch between the kernels of a step
     Buf hy_score, hy_len, hy_tok, hy_valid, hy_lo, hy_hi, err, dbg_ids, force_syms, a_hi, a_lo, splitk;
@@ -221,35 +221,24 @@ SplitOut split_of(const Act& a, int* overflow) {
 }
 
 void umma_launch(cudaStream_t s, int64_t M, int N, int K, const CUtensorMap& ahi, const CUtensorMap& alo, const CUtensorMap& whi,
-                 const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu, bool persistent) {
+                 const CUtensorMap& wlo, const float* bias, const Act& C, int ldc, bool gelu) {
     using SMm = UmmaSmem<kUmmaBN>;
-    dim3 grid((N + kUmmaBN - 1) / kUmmaBN, (unsigned)((M + UM - 1) / UM));
-    if (persistent) {
-        const int tiles = (int)(grid.x * grid.y);
-        const int ctas = std::min(tiles, sm_count());
-        const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;     // stream the larger operand once
-        if (gelu) {
-            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
-        } else {
-            CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-            umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
-        }
-        CUDA_CHECK(cudaGetLastError());
-        return;
-    }
+    const int tiles = (int)(((N + kUmmaBN - 1) / kUmmaBN) * ((M + UM - 1) / UM));
+    const int ctas = std::min(tiles, sm_count());
+    const int n_fastest = ((int64_t)M >= (int64_t)N) ? 1 : 0;     // stream the larger operand once
     if (gelu) {
-        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-        umma_gemm_tf32x3_kernel<kUmmaBN, true><<<grid, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+        umma_gemm_tf32x3_persistent_kernel<kUmmaBN, true><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
     } else {
-        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
-        umma_gemm_tf32x3_kernel<kUmmaBN, false><<<grid, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc);
+        CUDA_CHECK(cudaFuncSetAttribute(umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotal));
+        umma_gemm_tf32x3_persistent_kernel<kUmmaBN, false><<<ctas, UTHREADS2, SMm::kTotal, s>>>(ahi, alo, whi, wlo, (int)M, N, K, bias, C.x, C.hi, C.lo, ldc, n_fastest);
     }
     CUDA_CHECK(cudaGetLastError());
 }
 
-// C = A W^T + b (+GELU).  gemm_mode 1: 3xTF32 tcgen05 kernel on the pre-split operands (A.hi/A.lo
-// written by the producing kernel; split here only if the producer did not).  gemm_mode 0: fp32 SIMT.
+// C = A W^T + b (+GELU) on the tensor cores: gemm_mode 3 / 5 = 3xFP16 (one CTA per tile / CTA pairs), 2 = 3xTF32 (fp32
+// range: the fallback when an activation leaves the fp16 range).  Operands arrive pre-split from the producing kernel
+// (A.h1/A.h2 or A.hi/A.lo); they are split here only if the producer did not.
 void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu);
 
 void gemm(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, const Act& C, int ldc, bool gelu) {
@@ -268,7 +257,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
     if (M == 0) return;
     sealbart* m = cx.m;
     if (m->cfg.gemm_mode >= 3 && K % UK16 == 0 && lda == K && l.w_h1) {
-        const int rowb = m->cfg.gemm_mode == 4 ? 64 : 128;      // mode 5 (CTA pairs) shares mode 3's operand layout
+        constexpr int rowb = 128;                              // 128-byte shared-memory rows: 64 K-halves per k-block
         // 3xFP16 on tcgen05 (persistent); operands pre-split into halves by the producers
         const __half* a1 = A.h1; const __half* a2 = A.h2;
         if (!a1) {
@@ -342,8 +331,7 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
                 launch_k(kern, ctas2, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, nullptr, 1.0f, part, nullptr, nullptr,
                            ldc, n_fastest, ovf, k_slices, slice_stride);
             };
-            if (rowb == 128) launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
-            else launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>);
+            launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
             const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
             if (gelu) launch_k(umma_splitk_finish_kernel<true>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
@@ -355,12 +343,11 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMm::kTotalStaged));
             launch_k(kern, ctas, UTHREADS2, SMm::kTotalStaged, cx.s, ma1, ma2, l.map_hi, l.map_lo, (int)M, N, K, l.b, l.w_unscale, C.x, C.h1, C.h2, ldc, n_fastest, ovf, 1, (int64_t)0);
         };
-        if (rowb == 128) { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>); }
-        else { if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 64>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 64>); }
+        if (gelu) launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, true, 128>); else launch(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
         return;
     }
-    if (m->cfg.gemm_mode >= 1 && m->cfg.gemm_mode <= 2 && K % UK == 0 && lda == K && l.w_hi) {
+    if (m->cfg.gemm_mode == 2 && K % UK == 0 && lda == K && l.w_hi) {
         const float* ahi = A.hi; const float* alo = A.lo;
         if (!ahi) {
             m->a_hi.ensure((size_t)M * K * 4); m->a_lo.ensure((size_t)M * K * 4);
@@ -370,17 +357,11 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
         CUtensorMap mah, mal;
         make_map(&mah, ahi, M, K, K, UM); make_map(&mal, alo, M, K, K, UM);
         if (!l.maps_ready) { make_map(&l.map_hi, l.w_hi, N, K, K, kUmmaBN); make_map(&l.map_lo, l.w_lo, N, K, K, kUmmaBN); l.maps_ready = true; }
-        umma_launch(cx.s, M, N, K, mah, mal, l.map_hi, l.map_lo, l.b, C, ldc, gelu, m->cfg.gemm_mode == 2);
+        umma_launch(cx.s, M, N, K, mah, mal, l.map_hi, l.map_lo, l.b, C, ldc, gelu);
         m->launches++;
         return;
     }
-    if (K % GBK) throw ApiError(SEALFM_EINVAL, "GEMM K must be a multiple of 16");
-    if (!A.x || !C.x) throw ApiError(SEALFM_EINVAL, "internal: fp32 GEMM needs plain operands");
-    dim3 grid((N + GBN - 1) / GBN, (unsigned)((M + GBM - 1) / GBM));
-    if (gelu) sgemm_tn_kernel<true><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A.x, lda, l.w, K, l.b, C.x, ldc);
-    else sgemm_tn_kernel<false><<<grid, GTHREADS, 0, cx.s>>>((int)M, N, K, A.x, lda, l.w, K, l.b, C.x, ldc);
-    CUDA_CHECK(cudaGetLastError());
-    cx.m->launches++;
+    throw ApiError(SEALFM_EINVAL, "GEMM: K must be a multiple of 64 (3xFP16) / 32 (3xTF32) with contiguous operands");
 }
 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
@@ -480,7 +461,7 @@ void ensure_workspace(sealbart* m, const Dims& D) {
     m->st_anc.ensure(2 * D.R * D.T * 4); m->st_mask.ensure((size_t)2 * D.R * D.W * 4);
     m->st_rowmax.ensure(D.R * 4); m->st_rowls.ensure(D.R * 4); m->st_rule.ensure(D.R);
     m->st_cval.ensure((size_t)D.R * 2 * D.B * 4); m->st_cidx.ensure((size_t)D.R * 2 * D.B * 4); m->st_ccnt.ensure(D.R * 4);
-    if (m->cfg.gemm_mode >= 1) {
+    {
         m->ex_hi.ensure(Tk * D.d * 4); m->ex_lo.ensure(Tk * D.d * 4);
         m->eattn_hi.ensure(Tk * D.d * 4); m->eattn_lo.ensure(Tk * D.d * 4);
         m->effn_hi.ensure(Tk * D.f * 4); m->effn_lo.ensure(Tk * D.f * 4);
@@ -527,8 +508,8 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
     const int gm = m->cfg.gemm_mode;
     auto mk = [&](float* plain, Buf& bh, Buf& bl, bool keep_plain) {
         Act a;
-        if (gm == 0 || keep_plain) a.x = plain;
-        if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
+        if (keep_plain) a.x = plain;
+        if (gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
         if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
@@ -575,8 +556,8 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
     const int gm = m->cfg.gemm_mode;
     auto mk = [&](float* plain, Buf& bh, Buf& bl, bool keep_plain) {
         Act a;
-        if (gm == 0 || keep_plain) a.x = plain;
-        if (gm == 1 || gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
+        if (keep_plain) a.x = plain;
+        if (gm == 2) { a.hi = bh.as<float>(); a.lo = bl.as<float>(); }
         if (gm >= 3) { a.h1 = bh.as<__half>(); a.h2 = bl.as<__half>(); }
         return a;
     };
@@ -687,7 +668,9 @@ int sealbart_create(const sealbart_config_t* cfg, int device, sealbart_t** out) 
         if (!cfg || !out) throw ApiError(SEALFM_EINVAL, "null argument");
         if (cfg->d_model % 128 || cfg->d_model > 1024 || cfg->heads * kHeadDim != cfg->d_model)
             throw ApiError(SEALFM_EINVAL, "d_model must be a multiple of 128, <= 1024, with 64-wide heads");
-        if (cfg->ffn_dim % 16 || cfg->vocab_size <= 0) throw ApiError(SEALFM_EINVAL, "bad ffn_dim / vocab_size");
+        if (cfg->ffn_dim % 64 || cfg->vocab_size <= 0) throw ApiError(SEALFM_EINVAL, "bad ffn_dim / vocab_size");
+        if (cfg->gemm_mode != 2 && cfg->gemm_mode != 3 && cfg->gemm_mode != 5)
+            throw ApiError(SEALFM_EINVAL, "gemm_mode must be 5 (3xFP16 on CTA pairs, default), 3 (3xFP16, one CTA per tile) or 2 (3xTF32)");
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
         if (e != cudaSuccess || count == 0) { cudaGetLastError(); throw ApiError(SEALFM_ENODEVICE, "no CUDA device available"); }
@@ -750,7 +733,7 @@ int sealbart_finalize(sealbart_t* m) {
             if (!m->loaded.count(kv.first)) throw ApiError(SEALFM_EINVAL, "state_dict tensor missing: " + kv.first);
         if (!m->lm_head_given) m->lm_head = m->shared;          // tied (seal/utils.py:48-49)
         m->head.w = m->lm_head; m->head.b = m->final_bias; m->head.out = m->cfg.vocab_size; m->head.in = m->cfg.d_model;
-        if (m->cfg.gemm_mode >= 1) {
+        {
             CUDA_CHECK(cudaSetDevice(m->device));
             for (void* p : m->split_allocs) cudaFree(p);
             m->split_allocs.clear();
@@ -1058,8 +1041,8 @@ int sealbart_set_option(sealbart_t* m, const char* name, int64_t value) {
             check_model(m);
             if (value == m->cfg.gemm_mode) return;
             if (value == 2 && m->cfg.gemm_mode >= 3) { ensure_tf32_splits(m); m->cfg.gemm_mode = 2; }
-            else if (value >= 3 && value <= 5 && m->head.w_h1) m->cfg.gemm_mode = (int)value;
-            else throw ApiError(SEALFM_EINVAL, "gemm_mode can only switch between the 3xFP16 modes (3, 4, 5) and 2 (3xTF32)");
+            else if ((value == 3 || value == 5) && m->head.w_h1) m->cfg.gemm_mode = (int)value;
+            else throw ApiError(SEALFM_EINVAL, "gemm_mode can only switch between the 3xFP16 modes (3, 5) and 2 (3xTF32)");
             for_each_lin(m, [](Lin& l) { l.maps_ready = false; l.maps2_ready = false; });
             drop_graphs(m);
         }
@@ -1287,6 +1270,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         if (!A || !W || !C || M <= 0 || N <= 0 || K <= 0) throw ApiError(SEALFM_EINVAL, "bad argument");
         int count = 0;
         if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); throw ApiError(SEALFM_ENODEVICE, "no CUDA device available"); }
+        if (mode != 2 && mode != 3 && mode != 5) throw ApiError(SEALFM_EINVAL, "gemm_mode must be 2, 3 or 5");
         sealbart fake; fake.cfg.gemm_mode = mode;
         CUDA_CHECK(cudaGetDevice(&fake.device));
         Buf dA, dW, dB, dC, whi, wlo;
@@ -1298,7 +1282,7 @@ int sealdec_debug_gemm(int mode, int64_t M, int32_t N, int32_t K, const float* A
         if (bias) CUDA_CHECK(cudaMemcpy(dB.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
         Lin l; l.w = dW.as<float>(); l.b = bias ? dB.as<float>() : nullptr; l.out = N; l.in = K;
         fake.err.ensure(16); CUDA_CHECK(cudaMemset(fake.err.p, 0, 16)); fake.ovf = fake.err.as<int>() + 1;
-        if (mode == 1 || mode == 2) {
+        if (mode == 2) {
             whi.ensure((size_t)N * K * 4); wlo.ensure((size_t)N * K * 4);
             l.w_hi = whi.as<float>(); l.w_lo = wlo.as<float>();
             split_into(nullptr, l.w, l.w_hi, l.w_lo, (uint64_t)N * K);

@@ -223,18 +223,23 @@ __global__ void __launch_bounds__(256) order_pairs_kernel(uint32_t present_words
     if (threadIdx.x == 0) out_len[r] = 2ull * k;
 }
 
-// Measurement aid (sealfm_debug_sector_probe): independent random 32-byte sector reads over a buffer, four in flight
+// Measurement aid (sealfm_debug_sector_probe): independent random 32-byte sector reads over a buffer, eight in flight
 // per thread -- the memory system's ceiling for the access pattern of a rank query, the denominator the LF kernel's
 // beyond-L2 rate is compared with (a streaming-copy peak is not reachable with 32-byte random accesses).
 __global__ void __launch_bounds__(256) sector_probe_kernel(const uint4* __restrict__ buf, uint64_t n_sectors, uint64_t n_loads,
                                                            uint64_t seed, unsigned long long* __restrict__ sink) {
     auto mix = [](uint64_t x) { x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31); };
     uint32_t acc = 0;
-    for (uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 4; t < n_loads; t += (uint64_t)gridDim.x * blockDim.x * 4) {
-        const uint64_t i0 = mix(t + seed) % n_sectors, i1 = mix(t + 1 + seed) % n_sectors, i2 = mix(t + 2 + seed) % n_sectors, i3 = mix(t + 3 + seed) % n_sectors;
-        const uint4 a0 = __ldg(buf + 2 * i0), b0 = __ldg(buf + 2 * i0 + 1), a1 = __ldg(buf + 2 * i1), b1 = __ldg(buf + 2 * i1 + 1);
-        const uint4 a2 = __ldg(buf + 2 * i2), b2 = __ldg(buf + 2 * i2 + 1), a3 = __ldg(buf + 2 * i3), b3 = __ldg(buf + 2 * i3 + 1);
-        acc ^= a0.x ^ b0.w ^ a1.y ^ b1.z ^ a2.z ^ b2.y ^ a3.w ^ b3.x;
+    // index = hash * n_sectors >> 64 (no 64-bit division: the probe must be bound by the loads, not by the index arithmetic)
+    for (uint64_t t = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 8; t < n_loads; t += (uint64_t)gridDim.x * blockDim.x * 8) {
+        uint4 a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const uint64_t i = __umul64hi(mix(t + u + seed), n_sectors);
+            a[u] = __ldg(buf + 2 * i); b[u] = __ldg(buf + 2 * i + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc ^= a[u].x ^ b[u].w;
     }
     if (acc == 0xDEADBEEFu) atomicAdd(sink, 1ULL);              // keeps the loads alive
 }
@@ -745,7 +750,7 @@ int sealfm_extract_text(const sealfm_t* h, uint64_t n, const uint64_t* begins, c
 }
 
 /* Measurement aid: `n_loads` independent random 32-byte sector reads over a zero-filled device buffer of `buffer_bytes`
- * (4 in flight per thread); average device time per pass over `iters` passes (CUDA events). */
+ * (8 in flight per thread); average device time per pass over `iters` passes (CUDA events). */
 int sealfm_debug_sector_probe(uint64_t buffer_bytes, uint64_t n_loads, int iters, double* avg_us) {
     return guarded([&] {
         if (!avg_us || buffer_bytes < 64 || !n_loads || iters < 1) throw ApiError(SEALFM_EINVAL, "bad argument");
@@ -756,7 +761,7 @@ int sealfm_debug_sector_probe(uint64_t buffer_bytes, uint64_t n_loads, int iters
         CUDA_CHECK(cudaMemset(buf.p, 0, buffer_bytes));
         CUDA_CHECK(cudaMemset(sink.p, 0, 8));
         const uint64_t n_sectors = buffer_bytes / 32;
-        const int grid = sm_count() * 8;
+        const int grid = sm_count() * 8;                       // 2 048 threads per SM x 8 sectors each in flight
         sector_probe_kernel<<<grid, 256>>>((const uint4*)buf.p, n_sectors, n_loads, 1, sink.p);
         cudaEvent_t e0, e1; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
         CUDA_CHECK(cudaEventRecord(e0));

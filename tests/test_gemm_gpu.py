@@ -1,6 +1,6 @@
-"""GPU: the two GEMM back-ends of the BART path against a float64 reference of the same op
-(C = A W^T + b, optional exact GELU).  fp32 SIMT must be fp32-accurate; the 3xTF32 tcgen05 kernel
-must stay within a few fp32 ulps of it (that is what the 1e-4 beam-score parity rests on)."""
+"""GPU: the GEMM back-ends of the BART path -- 3xFP16 (one CTA per tile, CTA pairs) and the 3xTF32 range-safe fallback,
+all tcgen05 -- against a float64 reference of the same op (C = A W^T + b, optional exact GELU): they must stay within a
+few fp32 ulps of it (that is what the 1e-4 beam-score parity rests on)."""
 import ctypes as C
 import math
 
@@ -45,7 +45,7 @@ def test_gemm_cta_pair_matches_float64(M, N, K, gelu):
     test_gemm_matches_float64(5, M, N, K, gelu)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("M,N,K,gelu", SHAPES)
 def test_gemm_matches_float64(mode, M, N, K, gelu):
     rng = np.random.default_rng(M * 7 + N)
@@ -67,7 +67,7 @@ def test_gemm_throughput_report():
     for (M, N, K) in [(15000, 4096, 1024), (15000, 1024, 4096), (15000, 3072, 1024), (3000, 50265, 1024)]:
         A = rng.standard_normal((M, K)).astype(np.float32); W = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
         b = np.zeros(N, dtype=np.float32)
-        for mode in (0, 1, 2, 3, 4, 5):
+        for mode in (2, 3, 5):
             _, us = run_gemm(mode, A, W, b, False, iters=5)
             print(f"GEMM {M}x{N}x{K} mode {mode}: {us:.1f} us, {2.0 * M * N * K / us / 1e6:.1f} TFLOP/s (fp32-equivalent)")
 

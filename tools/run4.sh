@@ -15,4 +15,4 @@ for n in ("q20","q1000","q1000_oldattn","freq"):
     except Exception as e: print(n, "ERR", e)
 m=json.load(open("gpurun_out/r02_fm_microbench4.json")); print({k:round(v["expand_us"]) for k,v in m["walk_R15000"].items()})
 PY
-bash tools/ncu_r02.sh > $O/r02_ncu_script.log 2>&1; tail -12 $O/r02_ncu_script.log
+python bench.py --steps 5 --warmup 3 > $O/r02_bench4_full.json 2> $O/r02_bench4_full.err; tail -c 300 $O/r02_bench4_full.err
