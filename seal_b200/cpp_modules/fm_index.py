@@ -124,12 +124,15 @@ class FMIndex:
         return int(lib.sealfm_size(self._handle()))
 
     def backward_search_multi(self, query):                       # fm_index.cpp:55-65 -> [lo, hi_excl]
-        q = _u64(query)
-        offs = np.array([0, len(q)], dtype=np.uint64)
-        lo = np.zeros(1, dtype=np.uint64); hi = np.zeros(1, dtype=np.uint64)
-        check(lib.sealfm_backward_search_multi(self._dev(), 1, q.ctypes.data, offs.ctypes.data,
-                                               lo.ctypes.data, hi.ctypes.data))
-        return [int(lo[0]), int(hi[0])]
+        # one small buffer per call -- [symbols..., offsets(2), lo, hi] -- and one pointer lookup: seal/retrieval.py:91 issues
+        # this once per candidate key, so the Python-side cost counts as much as the kernel's
+        n = len(query)
+        buf = np.empty(n + 4, dtype=np.uint64)
+        buf[:n] = query
+        buf[n] = 0; buf[n + 1] = n
+        base = buf.ctypes.data
+        check(lib.sealfm_backward_search_multi(self._dev(), 1, base, base + 8 * n, base + 8 * (n + 2), base + 8 * (n + 3)))
+        return [int(buf[n + 2]), int(buf[n + 3])]
 
     def backward_search_step(self, symbol, low, high):            # fm_index.cpp:67-76 -> [lo', hi'_incl]
         s = np.array([symbol], dtype=np.uint64); l = np.array([low], dtype=np.uint64)

@@ -7,7 +7,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
-#include "pdl.cuh"
+#include "launch.cuh"
 
 namespace sealb200 {
 

@@ -6,7 +6,7 @@
 // host synchronisation.
 #pragma once
 #include "fm_device.cuh"
-#include "pdl.cuh"
+#include "launch.cuh"
 
 #include <cfloat>
 #include <cstdint>

@@ -121,6 +121,17 @@ def main():
     torch.cuda.synchronize(); t_ours = time.perf_counter() - t0
     out["e2e_batch20_ours"] = {"queries_per_s": 20 * nb / t_ours, "ms_per_batch": t_ours / nb * 1e3,
                                "what": "seal_b200.fm_index_generate (host arrays in, python list of hypotheses out)"}
+    # single-call latency of the drop-in API (seal/retrieval.py:91 filters keys with one get_count per key)
+    keys = [docs[i % len(docs), 3:3 + 1 + i % 4].tolist() for i in range(2000)]
+    for k in keys[:50]:
+        index.get_count(k)
+    t0 = time.perf_counter()
+    for k in keys:
+        index.get_count(k)
+    out["get_count_us_per_call"] = (time.perf_counter() - t0) / len(keys) * 1e6
+    t0 = time.perf_counter()
+    lo_b, hi_b = index.get_range_batch(keys)
+    out["get_range_batch_us_per_key"] = (time.perf_counter() - t0) / len(keys) * 1e6
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(out, f, indent=1)

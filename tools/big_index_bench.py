@@ -121,7 +121,7 @@ def main():
     _c(_l.sealfm_debug_sector_probe(int(index.device_bytes()), Nlf * 32, 5, C.byref(us)))
     ceil_gbps = Nlf * 32 * 32 / (us.value * 1e-6) / 1e9
     out["lf_random"] = {"triples": Nlf, "us": s * 1e6, "algorithmic_GBps": Nlf * 768 / s / 1e9, "frac_of_hbm_peak": Nlf * 768 / s / 1e9 / hbm, "hbm_peak_GBps": hbm,
-                        "sector_GBps": Nlf * 32 * 32 / s / 1e9, "random_sector_ceiling_GBps": ceil_gbps, "frac_of_random_sector_ceiling": (Nlf * 32 * 32 / s / 1e9) / ceil_gbps}
+                        "sector_GBps": Nlf * 32 * 32 / s / 1e9, "uniform_random_sector_GBps": ceil_gbps, "ratio_to_uniform_random_sector_rate": (Nlf * 32 * 32 / s / 1e9) / ceil_gbps}
     # count-proportional walk (what a trained model does): ranges from sampled corpus n-grams, expansion of their successor sets
     for R in (15000, 300):
         toks = torch.tensor(flat[prng.integers(0, n, size=R)].astype(np.int64) + 10, device=dev)
