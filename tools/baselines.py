@@ -36,8 +36,10 @@ def main():
     from seal_b200.cpp_modules.fm_index import FMIndex as RawFM
     from seal_b200.index import FMIndex
     from seal_b200.synthetic import corpus_symbols
-    torch.set_num_threads(os.cpu_count() or 1)
-    out = {"cpu_count": os.cpu_count()}
+    # the oracle loop does its score arithmetic with torch on the host: one thread per hardware thread is far too many for
+    # it (128 threads: 6.6 s per batch of 20; 16 threads: 0.5 s) -- same calibration as bench.py's baseline leg
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    out = {"cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}
     docs, ids, mask = build_inputs(args.queries, 4321)
     sym = corpus_symbols(docs)
     index = FMIndex(); RawFM.initialize(index, sym)
