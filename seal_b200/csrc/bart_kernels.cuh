@@ -166,10 +166,14 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
 // add+LN for SMALL row counts (batch 20: 300 rows): one CTA of 128 threads per row instead of one warp per row, so a row's
 // 4 KB are read by 128 threads at once and the kernel is not a chain of 8 dependent 16-byte loads per lane on 75 CTAs
 // (9.6 us per launch under ncu at 300 rows, 312 launches per generate: profiles/r02_f_launches_q20.csv).
+// With k_slices > 1, b is the raw split-K output of the preceding GEMM: b[r] = (sum_s part[s][r]) * unscale + bias, the
+// slices summed in index order exactly like umma_splitk_finish_kernel -- the finish launch of o / co / fc2 is folded in
+// (the same fold into the warp-per-row kernel was slower: 75 CTAs at 300 rows; here a row has its own 128 threads).
 __global__ void __launch_bounds__(128) add_ln_row_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                          const float* __restrict__ b, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ out,
-                                                         SplitOut so) {
+                                                         SplitOut so, int k_slices, int64_t slice_stride,
+                                                         const float* __restrict__ bias, float unscale) {
     __shared__ float red[2][4];
     const int64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -182,7 +186,15 @@ __global__ void __launch_bounds__(128) add_ln_row_kernel(int64_t rows, int d, co
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c4 < n4) {
             const float4 x = *reinterpret_cast<const float4*>(a + r * d + 4 * c4);
-            const float4 y = *reinterpret_cast<const float4*>(b + r * d + 4 * c4);
+            float4 y = *reinterpret_cast<const float4*>(b + r * d + 4 * c4);
+            if (k_slices > 1) {
+                for (int sl = 1; sl < k_slices; ++sl) {
+                    const float4 p = *reinterpret_cast<const float4*>(b + sl * slice_stride + r * d + 4 * c4);
+                    y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+                }
+                const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * c4);
+                y.x = y.x * unscale + bb.x; y.y = y.y * unscale + bb.y; y.z = y.z * unscale + bb.z; y.w = y.w * unscale + bb.w;
+            }
             v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }

@@ -166,7 +166,10 @@ void build_slots(sealbart* m) {
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------
-struct Ctx { sealbart* m; cudaStream_t s; };
+// pending: a split-K GEMM whose slices are still unsummed -- the add+LN that follows (small batches: add_ln_row_kernel)
+// folds the finish pass in
+struct PendingSplit { const float* part = nullptr; int ks = 0; int64_t stride = 0; const float* bias = nullptr; float unscale = 1.f; };
+struct Ctx { sealbart* m; cudaStream_t s; PendingSplit pending{}; bool defer_ok = false; };
 
 // ---- TMA descriptors ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -198,6 +201,7 @@ void make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t K, uint
 }
 
 constexpr int kUmmaBN = 256;
+constexpr int64_t kAddLnRowMax = 2048;      // up to this many rows add+LN runs one CTA per row
 
 void split_into(cudaStream_t s, const float* x, float* hi, float* lo, uint64_t numel) {
     const int64_t n4 = (int64_t)(numel / 4);
@@ -333,6 +337,10 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             };
             launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
+            if (cx.defer_ok && M <= kAddLnRowMax && !gelu && !C.h1 && !C.hi && ldc == N && l.b) {     // summed by the caller's add+LN
+                cx.pending = PendingSplit{part, k_slices, slice_stride, l.b, l.w_unscale};
+                return;
+            }
             const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
             if (gelu) launch_k(umma_splitk_finish_kernel<true>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
             else launch_k(umma_splitk_finish_kernel<false>, fblocks, 256, 0, cx.s, M, N, ldc, k_slices, slice_stride, part, l.b, l.w_unscale, C.x, C.h1, C.h2, ovf);
@@ -365,8 +373,11 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
 }
 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
-    if (rows <= 2048)          // small batches: a CTA per row
-        launch_k(add_ln_row_kernel, (unsigned)rows, 128, 0, cx.s, rows, d, a, b, (const float*)ln.g, (const float*)ln.b, out.x, split_of(out, cx.m->ovf));
+    const PendingSplit ps = cx.pending;
+    cx.pending = PendingSplit{};
+    if (rows <= kAddLnRowMax)          // small batches: a CTA per row (and the split-K finish of the GEMM before it, if pending)
+        launch_k(add_ln_row_kernel, (unsigned)rows, 128, 0, cx.s, rows, d, a, ps.ks > 1 ? ps.part : b, (const float*)ln.g, (const float*)ln.b, out.x,
+                 split_of(out, cx.m->ovf), ps.ks > 1 ? ps.ks : 1, ps.stride, ps.bias, ps.unscale);
     else
         launch_k(add_ln_kernel, (unsigned)((rows + 3) / 4), 128, 0, cx.s, rows, d, a, b, (const float*)ln.g, (const float*)ln.b, out.x, split_of(out, cx.m->ovf));
     cx.m->launches++;
@@ -531,10 +542,14 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
         gemm(cx, Te, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf), soff);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
+        cx.defer_ok = true;
         gemm(cx, Te, d, d, attn, d, L.o, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, Te, d, x.x, tmp.x, L.ln_attn, x);
         gemm(cx, Te, D.f, d, x, d, L.fc1, ffn, D.f, true);
+        cx.defer_ok = true;
         gemm(cx, Te, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, Te, d, x.x, tmp.x, L.ln_final, x);
     }
     // per-query cross-attention K/V of every decoder layer, once (the reference recomputes nothing
@@ -599,7 +614,9 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         else
             launch_k(dec_self_attn_long_kernel, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf));
         m->launches++;
+        cx.defer_ok = true;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
         const int64_t groups = D.grp_start ? D.G : D.Q;
@@ -612,10 +629,14 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
             launch_k(cross_attn_kernel, dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
                        ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x);
         m->launches++;
+        cx.defer_ok = true;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
         gemm(cx, R, D.f, d, x, d, L.fc1, ffn, D.f, true);
+        cx.defer_ok = true;
         gemm(cx, R, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
+        cx.defer_ok = false;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_final, x);
     }
     if (ev_layers_done) CUDA_CHECK(cudaEventRecord(ev_layers_done, cx.s));
