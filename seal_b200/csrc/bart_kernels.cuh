@@ -39,6 +39,31 @@ __device__ __forceinline__ void split4(const float4& v, float4& h, float4& l) {
 // fp32 arrays), 2 = FP16 (two half arrays; saturates at +-65504 and raises *overflow).
 struct SplitOut { void* a = nullptr; void* b = nullptr; int kind = 0; int* overflow = nullptr; };
 
+// A GEMM output that may still be in split-K form: ks > 1 -> value = (sum_s part[s * stride + off]) * unscale + bias[col],
+// the slices summed in index order exactly like umma_splitk_finish_kernel; ks <= 1 -> plain[off].  Lets the consumer of a
+// small-batch GEMM (add+LN, the attention kernels) do the finish pass itself instead of a separate launch.
+struct SplitSrc { const float* part = nullptr; int ks = 0; int64_t stride = 0; const float* bias = nullptr; float unscale = 1.f; };
+__device__ __forceinline__ float4 load_split4(const float* __restrict__ plain, const SplitSrc& ss, int64_t off, int col) {
+    if (ss.ks <= 1) return *reinterpret_cast<const float4*>(plain + off);
+    float4 y = *reinterpret_cast<const float4*>(ss.part + off);
+    for (int sl = 1; sl < ss.ks; ++sl) {
+        const float4 p = *reinterpret_cast<const float4*>(ss.part + sl * ss.stride + off);
+        y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+    }
+    const float4 bb = *reinterpret_cast<const float4*>(ss.bias + col);
+    return make_float4(y.x * ss.unscale + bb.x, y.y * ss.unscale + bb.y, y.z * ss.unscale + bb.z, y.w * ss.unscale + bb.w);
+}
+__device__ __forceinline__ float2 load_split2(const float* __restrict__ plain, const SplitSrc& ss, int64_t off, int col) {
+    if (ss.ks <= 1) return *reinterpret_cast<const float2*>(plain + off);
+    float2 y = *reinterpret_cast<const float2*>(ss.part + off);
+    for (int sl = 1; sl < ss.ks; ++sl) {
+        const float2 p = *reinterpret_cast<const float2*>(ss.part + sl * ss.stride + off);
+        y.x += p.x; y.y += p.y;
+    }
+    const float2 bb = *reinterpret_cast<const float2*>(ss.bias + col);
+    return make_float2(y.x * ss.unscale + bb.x, y.y * ss.unscale + bb.y);
+}
+
 __device__ __forceinline__ void half_split1(float x, __half& h1, __half& h2, int& ov) {
     if (fabsf(x) > 65504.f) { ov = 1; x = copysignf(65504.f, x); }
     h1 = __float2half_rn(x);
@@ -166,14 +191,12 @@ __global__ void __launch_bounds__(128) add_ln_kernel(int64_t rows, int d, const 
 // add+LN for SMALL row counts (batch 20: 300 rows): one CTA of 128 threads per row instead of one warp per row, so a row's
 // 4 KB are read by 128 threads at once and the kernel is not a chain of 8 dependent 16-byte loads per lane on 75 CTAs
 // (9.6 us per launch under ncu at 300 rows, 312 launches per generate: profiles/r02_f_launches_q20.csv).
-// With k_slices > 1, b is the raw split-K output of the preceding GEMM: b[r] = (sum_s part[s][r]) * unscale + bias, the
-// slices summed in index order exactly like umma_splitk_finish_kernel -- the finish launch of o / co / fc2 is folded in
+// bsrc: b may still be the raw split-K output of the preceding GEMM (SplitSrc) -- the finish launch of o / co / fc2 is folded in
 // (the same fold into the warp-per-row kernel was slower: 75 CTAs at 300 rows; here a row has its own 128 threads).
 __global__ void __launch_bounds__(128) add_ln_row_kernel(int64_t rows, int d, const float* __restrict__ a,
                                                          const float* __restrict__ b, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float* __restrict__ out,
-                                                         SplitOut so, int k_slices, int64_t slice_stride,
-                                                         const float* __restrict__ bias, float unscale) {
+                                                         SplitOut so, SplitSrc bsrc) {
     __shared__ float red[2][4];
     const int64_t r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -186,15 +209,7 @@ __global__ void __launch_bounds__(128) add_ln_row_kernel(int64_t rows, int d, co
         v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c4 < n4) {
             const float4 x = *reinterpret_cast<const float4*>(a + r * d + 4 * c4);
-            float4 y = *reinterpret_cast<const float4*>(b + r * d + 4 * c4);
-            if (k_slices > 1) {
-                for (int sl = 1; sl < k_slices; ++sl) {
-                    const float4 p = *reinterpret_cast<const float4*>(b + sl * slice_stride + r * d + 4 * c4);
-                    y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
-                }
-                const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * c4);
-                y.x = y.x * unscale + bb.x; y.y = y.y * unscale + bb.y; y.z = y.z * unscale + bb.z; y.w = y.w * unscale + bb.w;
-            }
+            const float4 y = load_split4(b, bsrc, r * d + 4 * c4, 4 * c4);
             v[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
             s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
         }
@@ -412,7 +427,7 @@ __host__ __device__ inline size_t self_attn_query_smem(int P, int B) { return (s
 __global__ void __launch_bounds__(1024) dec_self_attn_query_kernel(int64_t R, int B, int d, int cur_pos, int T,
                                                                   const float* __restrict__ qkv, float* kc, float* vc,
                                                                   const int32_t* __restrict__ anc,
-                                                                  float* __restrict__ out, SplitOut so) {
+                                                                  float* __restrict__ out, SplitOut so, SplitSrc qsrc) {
     extern __shared__ __align__(16) unsigned char sa_smem[];
     const int P = cur_pos + 1;
     float* Ks = reinterpret_cast<float*>(sa_smem);                       // [P][B][64]
@@ -447,8 +462,8 @@ __global__ void __launch_bounds__(1024) dec_self_attn_query_kernel(int64_t R, in
         const int a = row_of[s * 32 + slot];
         float4 kk, vv;
         if (s == cur_pos) {
-            const float* qp = qkv + (r0 + a) * 3 * d + col + 4 * i4;
-            kk = __ldg(reinterpret_cast<const float4*>(qp + d)); vv = __ldg(reinterpret_cast<const float4*>(qp + 2 * d));
+            const int64_t qoff = (r0 + a) * 3 * d + col + 4 * i4;
+            kk = load_split4(qkv, qsrc, qoff + d, d + col + 4 * i4); vv = load_split4(qkv, qsrc, qoff + 2 * d, 2 * d + col + 4 * i4);
             const int64_t off = ((int64_t)cur_pos * R + r0 + a) * d + col + 4 * i4;
             *reinterpret_cast<float4*>(kc + off) = kk; *reinterpret_cast<float4*>(vc + off) = vv;
         } else {
@@ -462,7 +477,7 @@ __global__ void __launch_bounds__(1024) dec_self_attn_query_kernel(int64_t R, in
     // ---- 3. warp b = beam b
     if (warp < B) {
         const int64_t r = r0 + warp;
-        const float2 q2 = __ldg(reinterpret_cast<const float2*>(qkv + r * 3 * d + col + 2 * lane));
+        const float2 q2 = load_split2(qkv, qsrc, r * 3 * d + col + 2 * lane, col + 2 * lane);
         float m = -INFINITY, l = 0.f, ax = 0.f, ay = 0.f;
         for (int s = 0; s < P; ++s) {
             const int slot = slot_of[s * 32 + warp];
@@ -640,7 +655,7 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
                                                                const int32_t* __restrict__ src_mask,
                                                                const int32_t* __restrict__ grp_query,
                                                                const int32_t* __restrict__ grp_start, float* __restrict__ out,
-                                                               SplitOut so, const int32_t* __restrict__ src_off) {
+                                                               SplitOut so, const int32_t* __restrict__ src_off, SplitSrc qsrc) {
     __shared__ __align__(16) float Ks[kXKeys][kXPad];
     __shared__ __align__(16) float Vs[kXKeys][kHeadDim];
     __shared__ __align__(16) float Qs[kXRows][kHeadDim];
@@ -672,7 +687,7 @@ __global__ void __launch_bounds__(128) cross_attn_small_kernel(int64_t G, int d,
         for (int e = tid; e < kXRows * (kHeadDim / 4); e += 128) {
             const int r = e / (kHeadDim / 4), i4 = e % (kHeadDim / 4);
             float4 qq = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rbase + r < rows) qq = *reinterpret_cast<const float4*>(q + (row0 + rbase + r) * d + head_off + 4 * i4);
+            if (rbase + r < rows) qq = load_split4(q, qsrc, (row0 + rbase + r) * d + head_off + 4 * i4, head_off + 4 * i4);
             *reinterpret_cast<float4*>(&Qs[r][4 * i4]) = qq;
         }
         __syncthreads();

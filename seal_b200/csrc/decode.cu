@@ -166,10 +166,9 @@ void build_slots(sealbart* m) {
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------
-// pending: a split-K GEMM whose slices are still unsummed -- the add+LN that follows (small batches: add_ln_row_kernel)
-// folds the finish pass in
-struct PendingSplit { const float* part = nullptr; int ks = 0; int64_t stride = 0; const float* bias = nullptr; float unscale = 1.f; };
-struct Ctx { sealbart* m; cudaStream_t s; PendingSplit pending{}; bool defer_ok = false; };
+// pending: a split-K GEMM whose slices are still unsummed -- its consumer (add+LN on small batches, the attention kernels)
+// folds the finish pass in; defer_rows = how many rows that consumer accepts (0: the GEMM must finish itself)
+struct Ctx { sealbart* m; cudaStream_t s; SplitSrc pending{}; int64_t defer_rows = 0; };
 
 // ---- TMA descriptors ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -337,8 +336,8 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
             };
             launch2(umma_gemm_f16x3_persistent_kernel<kUmmaBN, false, 128>);
             CUDA_CHECK(cudaGetLastError()); m->launches++;
-            if (cx.defer_ok && M <= kAddLnRowMax && !gelu && !C.h1 && !C.hi && ldc == N && l.b) {     // summed by the caller's add+LN
-                cx.pending = PendingSplit{part, k_slices, slice_stride, l.b, l.w_unscale};
+            if (M <= cx.defer_rows && !gelu && !C.h1 && !C.hi && ldc == N && l.b) {     // summed by the consumer kernel
+                cx.pending = SplitSrc{part, k_slices, slice_stride, l.b, l.w_unscale};
                 return;
             }
             const int fblocks = (int)std::min<int64_t>((M * (ldc / 4) + 255) / 256, (int64_t)sm_count() * 8);
@@ -373,11 +372,11 @@ void gemm_impl(Ctx& cx, int64_t M, int N, int K, const Act& A, int lda, Lin& l, 
 }
 
 void add_ln(Ctx& cx, int64_t rows, int d, const float* a, const float* b, const LNp& ln, const Act& out) {
-    const PendingSplit ps = cx.pending;
-    cx.pending = PendingSplit{};
+    const SplitSrc ps = cx.pending;
+    cx.pending = SplitSrc{};
     if (rows <= kAddLnRowMax)          // small batches: a CTA per row (and the split-K finish of the GEMM before it, if pending)
-        launch_k(add_ln_row_kernel, (unsigned)rows, 128, 0, cx.s, rows, d, a, ps.ks > 1 ? ps.part : b, (const float*)ln.g, (const float*)ln.b, out.x,
-                 split_of(out, cx.m->ovf), ps.ks > 1 ? ps.ks : 1, ps.stride, ps.bias, ps.unscale);
+        launch_k(add_ln_row_kernel, (unsigned)rows, 128, 0, cx.s, rows, d, a, b, (const float*)ln.g, (const float*)ln.b, out.x,
+                 split_of(out, cx.m->ovf), ps);
     else
         launch_k(add_ln_kernel, (unsigned)((rows + 3) / 4), 128, 0, cx.s, rows, d, a, b, (const float*)ln.g, (const float*)ln.b, out.x, split_of(out, cx.m->ovf));
     cx.m->launches++;
@@ -542,14 +541,14 @@ void encoder_forward(Ctx& cx, const Dims& D, const int64_t* ids_d, const int64_t
         gemm(cx, Te, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
         enc_self_attn_kernel<<<dim3((unsigned)D.Q, heads), kGAttnWarps * 32, 0, cx.s>>>(D.Q, d, heads, (int)D.S, qkv.x, m32, attn.x, split_of(attn, ovf), soff);
         CUDA_CHECK(cudaGetLastError()); m->launches++;
-        cx.defer_ok = true;
+        cx.defer_rows = kAddLnRowMax;
         gemm(cx, Te, d, d, attn, d, L.o, tmp, d, false);
-        cx.defer_ok = false;
+        cx.defer_rows = 0;
         add_ln(cx, Te, d, x.x, tmp.x, L.ln_attn, x);
         gemm(cx, Te, D.f, d, x, d, L.fc1, ffn, D.f, true);
-        cx.defer_ok = true;
+        cx.defer_rows = kAddLnRowMax;
         gemm(cx, Te, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
-        cx.defer_ok = false;
+        cx.defer_rows = 0;
         add_ln(cx, Te, d, x.x, tmp.x, L.ln_final, x);
     }
     // per-query cross-attention K/V of every decoder layer, once (the reference recomputes nothing
@@ -596,17 +595,22 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         DecLayerW& L = m->dec[l];
         float* kc = m->kc.as<float>() + (size_t)l * D.T * Rc * d;
         float* vc = m->vc.as<float>() + (size_t)l * D.T * Rc * d;
-        gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
-        const unsigned sa_threads = 32 * std::min(heads, 16);
         // the beams of a query together, distinct ancestors staged once (not at the compact first step, where a row
         // stands for all beams, nor for ragged re-scoring groups)
         static const bool sa_query = [] { const char* e = std::getenv("SEALB200_SELF_ATTN_QUERY"); return !e || std::atoi(e) != 0; }();
         const size_t saq_smem = self_attn_query_smem(pos + 1, D.B);
-        if (sa_query && !compact && !D.grp_start && pos >= 1 && D.B >= 2 && D.B <= 32 && pos + 1 <= 128 && saq_smem <= 112 * 1024) {
+        const bool use_saq = sa_query && !compact && !D.grp_start && pos >= 1 && D.B >= 2 && D.B <= 32 && pos + 1 <= 128 && saq_smem <= 112 * 1024;
+        cx.defer_rows = use_saq ? INT64_MAX : 0;               // that kernel sums a split-K qkv itself
+        gemm(cx, R, 3 * d, d, x, d, L.qkv, qkv, 3 * d, false);
+        cx.defer_rows = 0;
+        const SplitSrc qkv_src = cx.pending;
+        cx.pending = SplitSrc{};
+        const unsigned sa_threads = 32 * std::min(heads, 16);
+        if (use_saq) {
             static size_t saq_set = 0;
             if (saq_smem > saq_set) { CUDA_CHECK(cudaFuncSetAttribute(dec_self_attn_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024)); saq_set = 112 * 1024; }
             launch_k(dec_self_attn_query_kernel, dim3((unsigned)D.Q, heads), 32 * D.B, saq_smem, cx.s, Rc, D.B, d, pos, D.T, (const float*)qkv.x, kc, vc, anc,
-                     attn.x, split_of(attn, ovf));
+                     attn.x, split_of(attn, ovf), qkv_src);
         } else if (pos + 1 <= 12)
             launch_k(dec_self_attn_kernel<3>, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf), row_mul, row_mul);
         else if (pos + 1 <= 32)
@@ -614,29 +618,33 @@ void decoder_step(Ctx& cx, const Dims& D, const int32_t* tokens, int cur_len, co
         else
             launch_k(dec_self_attn_long_kernel, (unsigned)R, sa_threads, 0, cx.s, Rc, d, heads, pos, D.T, (const float*)qkv.x, kc, vc, anc, attn.x, split_of(attn, ovf));
         m->launches++;
-        cx.defer_ok = true;
+        cx.defer_rows = kAddLnRowMax;
         gemm(cx, R, d, d, attn, d, L.o, tmp, d, false);
-        cx.defer_ok = false;
+        cx.defer_rows = 0;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_self, x);
+        cx.defer_rows = (D.S <= kXKeys) ? INT64_MAX : 0;      // cross_attn_small_kernel sums a split-K cq itself
         gemm(cx, R, d, d, x, d, L.cq, cq, d, false);
+        cx.defer_rows = 0;
+        const SplitSrc cq_src = cx.pending;
+        cx.pending = SplitSrc{};
         const int64_t groups = D.grp_start ? D.G : D.Q;
         const float* ckv_l = m->ckv.as<float>() + (size_t)l * Tk * 2 * d;
         const int32_t* soff_x = m->enc_packed ? m->src_off.as<int32_t>() : nullptr;
         if (D.S <= kXKeys)
             launch_k(cross_attn_small_kernel, dim3((unsigned)groups, heads), 128, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
-                       ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x);
+                       ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x, cq_src);
         else
             launch_k(cross_attn_kernel, dim3((unsigned)groups, heads), kGAttnWarps * 32, 0, cx.s, groups, d, heads, compact ? 1 : D.B, (int)D.S, (const float*)cq.x,
                        ckv_l, m32, D.grp_query, D.grp_start, attn.x, split_of(attn, ovf), soff_x);
         m->launches++;
-        cx.defer_ok = true;
+        cx.defer_rows = kAddLnRowMax;
         gemm(cx, R, d, d, attn, d, L.co, tmp, d, false);
-        cx.defer_ok = false;
+        cx.defer_rows = 0;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_cross, x);
         gemm(cx, R, D.f, d, x, d, L.fc1, ffn, D.f, true);
-        cx.defer_ok = true;
+        cx.defer_rows = kAddLnRowMax;
         gemm(cx, R, d, D.f, ffn, D.f, L.fc2, tmp, d, false);
-        cx.defer_ok = false;
+        cx.defer_rows = 0;
         add_ln(cx, R, d, x.x, tmp.x, L.ln_final, x);
     }
     if (ev_layers_done) CUDA_CHECK(cudaEventRecord(ev_layers_done, cx.s));
