@@ -323,7 +323,6 @@ struct MergeShared {
     int tidx[kSelMaxK];
     uint8_t tvalid[kSelMaxK];
     float rv[kMergeThreads / 32]; int ri[kMergeThreads / 32]; int rslot[kMergeThreads / 32];
-    int tcount;
     int nbeam_src[kSelMaxBeams];          // candidate index feeding each new beam
     int n_noneos;
 };
@@ -374,14 +373,13 @@ __global__ void __launch_bounds__(kMergeThreads) select_merge_kernel(FmView fm, 
         }
         __syncthreads();
     }
-    if (tid == 0) S.tcount = want;
     if (tid < kSelMaxK) S.tvalid[tid] = tid < want ? 1 : 0;
     __syncthreads();
 
     // ---- fewer than K finite constrained candidates: fill with masked ones -------
     // torch.topk's choice among -inf ties is unspecified; ours: lowest flat index first.
-    if (tid == 0 && S.tcount < K) {
-        int have = S.tcount;
+    if (tid == 0 && want < K) {                                  // `want` is the same register value in every thread
+        int have = want;
         for (int flat = 0; have < K && flat < B * V; ++flat) {
             const int b = flat / V, v = flat - b * V;
             const int64_t r = r0 + b;
@@ -401,7 +399,6 @@ __global__ void __launch_bounds__(kMergeThreads) select_merge_kernel(FmView fm, 
             if (allowed && s > -INFINITY) continue;
             S.tval[have] = s; S.tidx[have] = flat; S.tvalid[have] = 0; ++have;
         }
-        S.tcount = have;
     }
     __syncthreads();
 
