@@ -1376,6 +1376,9 @@ int sealdec_apply_index_mask_d(const sealfm_t* fm, sealfm_stream_t stream, const
         }
         // scratch: lo, hi (u64), rule (u8), masks — stream-ordered allocation, no host sync
         uint64_t* lo = nullptr; uint64_t* hi = nullptr; uint8_t* rule = nullptr; uint32_t* masks = nullptr; uint64_t* fsyms = nullptr;
+        // stream-ordered frees on EVERY exit path (an ApiError / CUDA_CHECK below must not leak the scratch)
+        struct Scratch { void** p[5]; cudaStream_t s; ~Scratch() { for (void** q : p) if (*q) cudaFreeAsync(*q, s); } }
+            guard{{(void**)&lo, (void**)&hi, (void**)&rule, (void**)&masks, (void**)&fsyms}, s};
         CUDA_CHECK(cudaMallocAsync(&lo, R * 8, s)); CUDA_CHECK(cudaMallocAsync(&hi, R * 8, s));
         CUDA_CHECK(cudaMallocAsync(&rule, R, s)); CUDA_CHECK(cudaMallocAsync(&masks, (size_t)R * W * 4, s));
         const int nf = cfg->n_force_decoding_from;
@@ -1395,8 +1398,6 @@ int sealdec_apply_index_mask_d(const sealfm_t* fm, sealfm_stream_t stream, const
         apply_mask_kernel<<<grid, 256, 0, s>>>(R, (int)V, ld, in_d, out_d, masks, W, 0, rule, cfg->eos_token_id,
                                                cfg->pad_token_id, cfg->always_allow_eos, -1);
         CUDA_CHECK(cudaGetLastError());
-        cudaFreeAsync(lo, s); cudaFreeAsync(hi, s); cudaFreeAsync(rule, s); cudaFreeAsync(masks, s);
-        if (fsyms) cudaFreeAsync(fsyms, s);
     });
 }
 
